@@ -1,0 +1,215 @@
+/*
+ * mocc_b200.h -- C ABI of the B200-native MoC transport sweep.
+ *
+ * This is the drop-in boundary: the only thing the host
+ * side (the C++ TransportSweeper subclass in mocc_b200/host/, or any FFI such as
+ * the ctypes binding in mocc_b200/capi.py) ever calls. Plain pointers and sizes,
+ * caller-owned host buffers, callee-owned device memory, int status codes, no
+ * exceptions and no torch/C++ types across the boundary.
+ *
+ * Reference interfaces replaced (all under /root/reference/src):
+ *   mocb200_create            <- moc::MoCSweeper::MoCSweeper          sweepers/moc/moc_sweeper.cpp:62-187
+ *                                (device copy of RayData / BoundaryCondition layout / Exponential_Linear)
+ *   mocb200_set_xs            <- ExpandedXS::expand                   core/xs_mesh.hpp:261-298
+ *   mocb200_set_source        <- Source::get() handed to self_scatter core/source.hpp:150-153
+ *   mocb200_set_flux/get_flux <- TransportSweeper::flux_ column       core/transport_sweeper.hpp:139-150
+ *   mocb200_set/get_boundary  <- BoundaryCondition::data_             core/boundary_condition.hpp:144-164
+ *   mocb200_sweep             <- MoCSweeper::sweep + sweep1g<CW>      sweepers/moc/moc_sweeper.cpp:189-225,
+ *                                + SourceIsotropic::self_scatter      sweepers/moc/moc_sweeper_kernel.inc.hpp:36-180,
+ *                                + BoundaryCondition::update          core/source_isotropic.cpp:21-57,
+ *                                                                     core/boundary_condition.cpp:145-191
+ *   mocb200_get_coarse        <- moc::Current::post_ray tallies       sweepers/moc/moc_current_worker.hpp:202-264
+ *   mocb200_get_corrections   <- cmdo::CurrentCorrections tallies     sweepers/cmdo/correction_worker.hpp:109-246
+ *
+ * All floating point data is FP64, all indices int32 unless stated (the
+ * reference: real_t = double, util/global_config.hpp:27-33).
+ */
+#ifndef MOCC_B200_H
+#define MOCC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOCB200_MAX_POLAR 4 /* polar angles that may share one geometry bundle */
+
+/* status codes */
+#define MOCB200_OK 0
+#define MOCB200_ERR_INVALID 1 /* bad argument / inconsistent problem description */
+#define MOCB200_ERR_CUDA 2    /* CUDA runtime error, see mocb200_last_error */
+#define MOCB200_ERR_NO_DEVICE 3
+#define MOCB200_ERR_STATE 4   /* call sequence error (e.g. sweep before set_xs) */
+
+/* tally modes of mocb200_sweep (what the LAST inner iteration accumulates) */
+#define MOCB200_TALLY_NONE 0        /* moc::NoCurrent */
+#define MOCB200_TALLY_CURRENT 1     /* moc::Current: coarse currents + surface flux */
+#define MOCB200_TALLY_CORRECTIONS 2 /* cmdo::CurrentCorrections (2D3D) */
+
+/* boundary update schemes (MoCSweeper attribute boundary_update, moc_sweeper.cpp:105-116) */
+#define MOCB200_BOUNDARY_GS 0     /* reference default; two phases (octant 1+3, then 2+4) */
+#define MOCB200_BOUNDARY_JACOBI 1 /* all angles from the previous sweep's outgoing flux */
+
+/* exponential evaluation */
+#define MOCB200_EXP_TABLE 0    /* Exponential_Linear<N> table in shared memory, bit-identical entries */
+#define MOCB200_EXP_FACTORED 1 /* same grid + linear interpolation, grid values from two bank-replicated
+                                  factor tables (<= 2 ulp from the table entries) */
+
+/*
+ * Flattened ray-tracing data ("MOCFLAT"), produced once on the host from the
+ * reference's RayData / CoreMesh / AngularQuadrature objects
+ * (mocc_b200/host/flatten.cpp). Field names equal the array names of the
+ * .mocflat container so that any FFI can fill this struct mechanically.
+ *
+ * Angle indexing follows the reference: sweep angle a in [0, n_ang) covers
+ * octants 1-2 (n_ang = 2*ndir_oct), its reverse is a + n_ang; boundary storage
+ * covers n_ang_bc = 4*ndir_oct angles.
+ */
+typedef struct mocb200_problem {
+    /* ---- scalars ---- */
+    int32_t n_group;
+    int32_t n_reg;        /* FSRs over all macroplanes (MeshTreatment::PLANE) */
+    int32_t n_plane;      /* macroplanes */
+    int32_t n_unique;     /* geometrically unique planes (ray sets) */
+    int32_t ndir_oct;
+    int32_t n_ang;        /* 2*ndir_oct */
+    int32_t n_geom;       /* distinct ray geometries among the n_ang sweep angles */
+    int32_t bc_per_group; /* boundary values per group per plane */
+    int32_t n_surf;       /* coarse surfaces, whole mesh */
+    int32_t n_cell;       /* coarse cells, whole mesh */
+    int32_t n_surf_plane; /* coarse surfaces per plane */
+    int32_t n_cell_plane; /* coarse cells per plane (nx*ny) */
+    int32_t nx, ny, nz;   /* coarse mesh dimensions */
+    int32_t exp_n;        /* Exponential_Linear<N>: intervals (10000) */
+    double exp_min;       /* -10.0 */
+    double exp_max;       /*   0.0 */
+    int64_t n_trk;        /* tracks: unique (unique plane, geometry, ray) */
+    int64_t n_seg;        /* segments over all tracks */
+    int64_t n_cm;         /* coarse-ray records over all tracks */
+
+    /* ---- per sweep angle [n_ang] ---- */
+    const int32_t *ang_geom;     /* geometry id of the angle */
+    const double *ang_rsintheta; /* Direction::rsintheta (long double trig), kernel:79 */
+    /* ---- per (macroplane, sweep angle) [n_plane*n_ang] ---- */
+    const double *wt_v_st;       /* weight*spacing*height*sin(theta)*PI, kernel:80-82 */
+    const double *cur_wx, *cur_wy; /* moc::Current current_weights_[0/1], moc_current_worker.hpp:192-195 */
+    const double *flx_wx, *flx_wy; /* flux_weights_[0/1], :196-197 */
+
+    /* ---- boundary-condition layout [n_ang_bc = 2*n_ang] ---- */
+    const int32_t *bc_offset;   /* start of the angle's block inside one group, boundary_condition.cpp:63-74 */
+    const int32_t *bc_size_x;   /* slots on the X-normal face (= RayData::ny) */
+    const int32_t *bc_size_y;   /* slots on the Y-normal face (= RayData::nx) */
+    const int32_t *bc_dst_off;  /* [n_ang_bc*2] offset of the face this angle's outgoing face (X,Y) feeds */
+    const int32_t *bc_dst_kind; /* [n_ang_bc*2] 0 vacuum (write 0), 1 reflect (copy), 2 prescribed (keep) */
+
+    /* ---- geometry: tracks ---- */
+    const int64_t *geom_trk_begin; /* [n_unique*n_geom + 1] CSR over tracks */
+    const int64_t *trk_seg_begin;  /* [n_trk + 1] CSR over segments */
+    const int32_t *trk_bc;         /* [n_trk*2] Ray::bc(0), Ray::bc(1) */
+    const int64_t *trk_cm_begin;   /* [n_trk + 1] CSR over coarse-ray records */
+    const int32_t *trk_cm_start;   /* [n_trk*4] cm_cell_fw, cm_cell_bw, cm_surf_fw, cm_surf_bw (plane-local) */
+    const double *seg_len;         /* [n_seg] Ray::seg_len (after volume correction) */
+    const int32_t *seg_fsr;        /* [n_seg] Ray::seg_index (plane-local FSR) */
+    const uint32_t *cm_data;       /* [n_cm] fw | bw<<4 | nseg_fw<<8 | nseg_bw<<16 (Ray::RayCoarseData) */
+
+    /* ---- macroplanes [n_plane] ---- */
+    const int32_t *plane_unique;      /* ray-set id, MoCSweeper::macroplane_unique_ids_ */
+    const int32_t *plane_first_reg;   /* first_reg_macroplane_ */
+    const int32_t *plane_cell_offset; /* Mesh::coarse_cell_offset(iplane) */
+    const int32_t *plane_surf_offset; /* Mesh::coarse_surf_offset(iplane) */
+
+    /* ---- coarse mesh, one plane [n_cell_plane*4], surfaces E,N,W,S ---- */
+    const int32_t *coarse_surf; /* Mesh::coarse_surf(cell, s), plane-local */
+    const int32_t *coarse_nbr;  /* Mesh::coarse_neighbor(cell, s), -1 outside */
+
+    /* ---- FSR data [n_reg] ---- */
+    const double *vol; /* TransportSweeper::vol_ */
+
+    /* ---- exponential table [exp_n + 2]: exp(exp_min + i*space), last entry repeated ---- */
+    const double *exp_table;
+} mocb200_problem;
+
+typedef struct mocb200_sweeper mocb200_sweeper; /* opaque */
+
+/* Options fixed at creation */
+typedef struct mocb200_options {
+    int32_t device;          /* CUDA device ordinal */
+    int32_t boundary_update; /* MOCB200_BOUNDARY_* */
+    int32_t exp_mode;        /* MOCB200_EXP_* */
+    int32_t max_polar;       /* polar angles bundled per work item (1..MOCB200_MAX_POLAR); 0 = default */
+    int32_t block_threads;   /* 0 = default */
+    int32_t plane_begin;     /* this rank's macroplane range [plane_begin, plane_end); both 0 = all */
+    int32_t plane_end;
+    int32_t reserved[9];
+} mocb200_options;
+
+/* Build the device-resident problem. The host arrays may be freed afterwards. */
+int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb200_sweeper **out);
+int mocb200_destroy(mocb200_sweeper *h);
+/* Message for the last non-OK status of this handle (or of create when h is NULL). */
+const char *mocb200_last_error(const mocb200_sweeper *h);
+/* Use a caller-provided cudaStream_t for all subsequent work (NULL = handle's own stream). */
+int mocb200_set_stream(mocb200_sweeper *h, void *cuda_stream);
+int mocb200_synchronize(mocb200_sweeper *h);
+
+/*
+ * Per-group data. Host arrays are [g_count][n_reg] (one contiguous column per
+ * group, groups g_begin .. g_begin+g_count-1).
+ *   xstr      transport XS the sweep attenuates with (ExpandedXS incl. TL splitting)
+ *   xstr_src  transport XS used in the source normalisation q/(4 pi xstr_src); the
+ *             reference uses the UN-split XS there (source_isotropic.cpp:29); NULL = xstr
+ *   xs_self   within-group scattering XS Sigma_s(g->g) per FSR (source_isotropic.cpp:30)
+ */
+int mocb200_set_xs(mocb200_sweeper *h, int g_begin, int g_count, const double *xstr,
+                   const double *xstr_src, const double *xs_self);
+/* 1-group source WITHOUT self scatter (fission + in-scatter + external), Source::get() */
+int mocb200_set_source(mocb200_sweeper *h, int g_begin, int g_count, const double *src);
+int mocb200_set_flux(mocb200_sweeper *h, int g_begin, int g_count, const double *flux);
+int mocb200_get_flux(mocb200_sweeper *h, int g_begin, int g_count, double *flux);
+/* Directly impose q-bar (skips self scatter on the next sweep with n_inner == 1 and
+ * use_qbar != 0); for sweep1g-level parity tests. [g_count][n_reg] */
+int mocb200_set_qbar(mocb200_sweeper *h, int g_begin, int g_count, const double *qbar);
+
+/* Incoming boundary flux of one macroplane: [g_count][bc_per_group], reference layout. */
+int mocb200_set_boundary(mocb200_sweeper *h, int plane, int g_begin, int g_count, const double *bc);
+int mocb200_get_boundary(mocb200_sweeper *h, int plane, int g_begin, int g_count, double *bc);
+
+/*
+ * The hot path. For groups [g_begin, g_begin+g_count) run n_inner inner iterations:
+ *   q-bar = (src + flux*xs_self) / (4 pi xstr_src)   (unless use_qbar)
+ *   transport sweep over all rays/angles/planes of this handle, boundary update
+ *   flux = tally/(xstr*vol) + 4 pi q-bar
+ * The last inner also accumulates the tallies selected by tally_mode.
+ * Asynchronous on the handle's stream.
+ */
+int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int tally_mode, int use_qbar);
+
+/* Raw radial coarse tallies of the last TALLY_CURRENT/CORRECTIONS sweep for one group:
+ * current[n_surf], surface_flux[n_surf] (whole-mesh surface indexing, x/y-normal surfaces of
+ * this handle's macroplanes only, NOT yet divided by the surface area -- the reference does
+ * that in post_sweep, moc_current_worker.hpp:272-318). */
+int mocb200_get_coarse(mocb200_sweeper *h, int group, double *current, double *surface_flux);
+
+/* Counters for bench/diagnostics */
+typedef struct mocb200_stats {
+    int64_t kernel_launches;   /* kernels launched by this handle since creation */
+    int64_t sweep_launches;    /* of which transport-sweep kernels */
+    int64_t segments_per_sweep; /* reference segment count S (per-polar copies counted), this handle's planes */
+    int64_t unique_segments;   /* segments resident on the device */
+    int64_t device_bytes;      /* device memory held */
+    int64_t items[2];          /* work items (track, direction) per boundary phase */
+} mocb200_stats;
+int mocb200_get_stats(const mocb200_sweeper *h, mocb200_stats *out);
+
+/* Time (ms, CUDA events on the handle's stream) spent in transport-sweep kernels by the last
+ * mocb200_sweep call; synchronises. */
+int mocb200_last_sweep_ms(mocb200_sweeper *h, double *ms);
+
+/* Library/version string */
+const char *mocb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOCC_B200_H */

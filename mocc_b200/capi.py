@@ -1,0 +1,242 @@
+"""ctypes binding of the C ABI declared in ``include/mocc_b200.h``.
+
+This is the FFI a Python host would use; the C++ plugin in ``mocc_b200/host/``
+calls the very same entry points.  There is NO CPU fallback: if the CUDA
+library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .flatfile import scalar
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libmocc_b200.so")
+
+MAX_POLAR = 4
+TALLY_NONE, TALLY_CURRENT, TALLY_CORRECTIONS = 0, 1, 2
+BOUNDARY_GS, BOUNDARY_JACOBI = 0, 1
+EXP_TABLE, EXP_FACTORED = 0, 1
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u32p = C.POINTER(C.c_uint32)
+_f64p = C.POINTER(C.c_double)
+
+# (field name, ctype) in the exact order of struct mocb200_problem
+_SCALARS = [
+    ("n_group", C.c_int32), ("n_reg", C.c_int32), ("n_plane", C.c_int32), ("n_unique", C.c_int32),
+    ("ndir_oct", C.c_int32), ("n_ang", C.c_int32), ("n_geom", C.c_int32), ("bc_per_group", C.c_int32),
+    ("n_surf", C.c_int32), ("n_cell", C.c_int32), ("n_surf_plane", C.c_int32), ("n_cell_plane", C.c_int32),
+    ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("exp_n", C.c_int32),
+    ("exp_min", C.c_double), ("exp_max", C.c_double),
+    ("n_trk", C.c_int64), ("n_seg", C.c_int64), ("n_cm", C.c_int64),
+]
+_ARRAYS = [
+    ("ang_geom", _i32p), ("ang_rsintheta", _f64p),
+    ("wt_v_st", _f64p), ("cur_wx", _f64p), ("cur_wy", _f64p), ("flx_wx", _f64p), ("flx_wy", _f64p),
+    ("bc_offset", _i32p), ("bc_size_x", _i32p), ("bc_size_y", _i32p), ("bc_dst_off", _i32p),
+    ("bc_dst_kind", _i32p),
+    ("geom_trk_begin", _i64p), ("trk_seg_begin", _i64p), ("trk_bc", _i32p), ("trk_cm_begin", _i64p),
+    ("trk_cm_start", _i32p), ("seg_len", _f64p), ("seg_fsr", _i32p), ("cm_data", _u32p),
+    ("plane_unique", _i32p), ("plane_first_reg", _i32p), ("plane_cell_offset", _i32p),
+    ("plane_surf_offset", _i32p),
+    ("coarse_surf", _i32p), ("coarse_nbr", _i32p),
+    ("vol", _f64p), ("exp_table", _f64p),
+]
+_NP = {_i32p: np.int32, _i64p: np.int64, _u32p: np.uint32, _f64p: np.float64}
+
+
+class Problem(C.Structure):
+    _fields_ = _SCALARS + _ARRAYS
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("boundary_update", C.c_int32), ("exp_mode", C.c_int32),
+                ("max_polar", C.c_int32), ("block_threads", C.c_int32), ("plane_begin", C.c_int32),
+                ("plane_end", C.c_int32), ("reserved", C.c_int32 * 9)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("sweep_launches", C.c_int64),
+                ("segments_per_sweep", C.c_int64), ("unique_segments", C.c_int64),
+                ("device_bytes", C.c_int64), ("items", C.c_int64 * 2)]
+
+
+def problem_from_arrays(arrays):
+    """Build a ``Problem`` struct viewing the numpy arrays of a flattened problem.
+
+    Returns (struct, keepalive list); the arrays must outlive the struct's use.
+    """
+    p = Problem()
+    keep = []
+    for name, ct in _SCALARS:
+        if name == "n_trk":
+            v = arrays["trk_bc"].size // 2
+        elif name == "n_seg":
+            v = arrays["seg_len"].size
+        elif name == "n_cm":
+            v = arrays["cm_data"].size
+        else:
+            v = scalar(arrays, name)
+        setattr(p, name, v)
+    for name, ct in _ARRAYS:
+        a = np.ascontiguousarray(arrays[name], dtype=_NP[ct]).reshape(-1)
+        if a.size == 0:
+            a = np.zeros(1, dtype=_NP[ct])
+        keep.append(a)
+        setattr(p, name, a.ctypes.data_as(ct))
+    return p, keep
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"mocc_b200: CUDA library not found at {path}; build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    lib = C.CDLL(path)
+    H = C.c_void_p
+    lib.mocb200_create.argtypes = [C.POINTER(Problem), C.POINTER(Options), C.POINTER(H)]
+    lib.mocb200_destroy.argtypes = [H]
+    lib.mocb200_last_error.argtypes = [H]
+    lib.mocb200_last_error.restype = C.c_char_p
+    lib.mocb200_set_stream.argtypes = [H, C.c_void_p]
+    lib.mocb200_synchronize.argtypes = [H]
+    lib.mocb200_set_xs.argtypes = [H, C.c_int, C.c_int, _f64p, _f64p, _f64p]
+    for fn in ("mocb200_set_source", "mocb200_set_flux", "mocb200_get_flux", "mocb200_set_qbar"):
+        getattr(lib, fn).argtypes = [H, C.c_int, C.c_int, _f64p]
+    lib.mocb200_set_boundary.argtypes = [H, C.c_int, C.c_int, C.c_int, _f64p]
+    lib.mocb200_get_boundary.argtypes = [H, C.c_int, C.c_int, C.c_int, _f64p]
+    lib.mocb200_sweep.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.mocb200_get_coarse.argtypes = [H, C.c_int, _f64p, _f64p]
+    lib.mocb200_get_stats.argtypes = [H, C.POINTER(Stats)]
+    lib.mocb200_last_sweep_ms.argtypes = [H, _f64p]
+    lib.mocb200_version.restype = C.c_char_p
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_f64p)
+
+
+def _host(a, shape):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.shape != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+class Sweeper:
+    """Handle on a device-resident MoC problem (one GPU)."""
+
+    def __init__(self, arrays, device=0, boundary_update=BOUNDARY_GS, exp_mode=EXP_TABLE, max_polar=0,
+                 block_threads=0, plane_begin=0, plane_end=0, lib=None):
+        self.lib = lib or load_library()
+        self.arrays = arrays
+        self.problem, self._keep = problem_from_arrays(arrays)
+        self.n_group = self.problem.n_group
+        self.n_reg = self.problem.n_reg
+        self.n_plane = self.problem.n_plane
+        self.n_surf = self.problem.n_surf
+        self.bc_per_group = self.problem.bc_per_group
+        opt = Options()
+        opt.device, opt.boundary_update, opt.exp_mode = device, boundary_update, exp_mode
+        opt.max_polar, opt.block_threads = max_polar, block_threads
+        opt.plane_begin, opt.plane_end = plane_begin, plane_end
+        self.h = C.c_void_p()
+        rc = self.lib.mocb200_create(C.byref(self.problem), C.byref(opt), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.mocb200_last_error(None).decode()
+            self.h = None
+            raise RuntimeError(f"mocb200_create failed ({rc}): {msg}")
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.mocb200_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mocb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.mocb200_set_stream(self.h, C.c_void_p(cuda_stream)), "set_stream")
+
+    def synchronize(self):
+        self._ck(self.lib.mocb200_synchronize(self.h), "synchronize")
+
+    def set_xs(self, g_begin, xstr, xstr_src=None, xs_self=None):
+        xstr = np.ascontiguousarray(xstr, dtype=np.float64).reshape(-1, self.n_reg)
+        gc = xstr.shape[0]
+        src = None if xstr_src is None else _host(np.reshape(xstr_src, (-1, self.n_reg)), (gc, self.n_reg))
+        if xs_self is None:
+            xs_self = np.zeros((gc, self.n_reg))
+        slf = _host(np.reshape(xs_self, (-1, self.n_reg)), (gc, self.n_reg))
+        self._ck(self.lib.mocb200_set_xs(self.h, g_begin, gc, _ptr(xstr),
+                                         _ptr(src) if src is not None else None, _ptr(slf)), "set_xs")
+
+    def _set(self, fn, g_begin, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, self.n_reg)
+        self._ck(getattr(self.lib, fn)(self.h, g_begin, a.shape[0], _ptr(a)), fn)
+
+    def set_source(self, g_begin, src):
+        self._set("mocb200_set_source", g_begin, src)
+
+    def set_flux(self, g_begin, flux):
+        self._set("mocb200_set_flux", g_begin, flux)
+
+    def set_qbar(self, g_begin, qbar):
+        self._set("mocb200_set_qbar", g_begin, qbar)
+
+    def get_flux(self, g_begin, g_count, out=None):
+        if out is None:
+            out = np.empty((g_count, self.n_reg))
+        self._ck(self.lib.mocb200_get_flux(self.h, g_begin, g_count, _ptr(out)), "get_flux")
+        return out
+
+    def set_boundary(self, plane, g_begin, bc):
+        bc = np.ascontiguousarray(bc, dtype=np.float64).reshape(-1, self.bc_per_group)
+        self._ck(self.lib.mocb200_set_boundary(self.h, plane, g_begin, bc.shape[0], _ptr(bc)), "set_boundary")
+
+    def get_boundary(self, plane, g_begin, g_count):
+        out = np.empty((g_count, self.bc_per_group))
+        self._ck(self.lib.mocb200_get_boundary(self.h, plane, g_begin, g_count, _ptr(out)), "get_boundary")
+        return out
+
+    def sweep(self, g_begin, g_count, n_inner=1, tally_mode=TALLY_NONE, use_qbar=False):
+        self._ck(self.lib.mocb200_sweep(self.h, g_begin, g_count, n_inner, tally_mode, int(use_qbar)), "sweep")
+
+    def get_coarse(self, group):
+        cur = np.zeros(self.n_surf)
+        sf = np.zeros(self.n_surf)
+        self._ck(self.lib.mocb200_get_coarse(self.h, group, _ptr(cur), _ptr(sf)), "get_coarse")
+        return cur, sf
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.lib.mocb200_get_stats(self.h, C.byref(s)), "get_stats")
+        return {"kernel_launches": s.kernel_launches, "sweep_launches": s.sweep_launches,
+                "segments_per_sweep": s.segments_per_sweep, "unique_segments": s.unique_segments,
+                "device_bytes": s.device_bytes, "items": [s.items[0], s.items[1]]}
+
+    def last_sweep_ms(self):
+        ms = C.c_double()
+        self._ck(self.lib.mocb200_last_sweep_ms(self.h, C.byref(ms)), "last_sweep_ms")
+        return ms.value

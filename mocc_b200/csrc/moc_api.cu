@@ -1,0 +1,741 @@
+// moc_api.cu -- the C ABI of include/mocc_b200.h: host-side set-up (work lists,
+// coarse-crossing lists, uploads) and kernel orchestration. See moc_kernels.cuh for
+// the device code and the execution model.
+#include "mocc_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "moc_kernels.cuh"
+
+using namespace mocb200;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceBuf {
+    void *p      = nullptr;
+    size_t bytes = 0;
+};
+
+struct WorkList { // one kernel launch: items of one (unique plane, boundary phase, polar count)
+    int unique = 0, phase = 0, np = 0;
+    Item *d_items    = nullptr;
+    int32_t n_items  = 0;
+    int32_t *d_planes = nullptr;
+    int32_t n_planes = 0;
+    int64_t segs     = 0; // segments walked per group by this list (all its planes)
+};
+
+} // namespace
+
+struct mocb200_sweeper {
+    int device = 0;
+    mocb200_options opt{};
+    // dims
+    int G = 0, GP = 0, n_reg = 0, n_plane = 0, n_ang = 0, bcpg = 0, n_surf = 0, n_surf_plane = 0;
+    int plane_begin = 0, plane_end = 0;
+    int reg_lo = 0, reg_hi = 0; // FSR range of this handle's planes
+    int exp_n = 0;
+    double exp_min = 0, exp_max = 0;
+    int sm_count = 148;
+    // device memory
+    std::vector<void *> allocs;
+    int64_t device_bytes = 0;
+    double *d_seg_len = nullptr;
+    int32_t *d_seg_fsr = nullptr;
+    Cross *d_cross     = nullptr;
+    Bundle *d_bundles  = nullptr;
+    double *d_rsin = nullptr, *d_wt = nullptr, *d_curw = nullptr, *d_flxw = nullptr;
+    int32_t *d_bc_offset = nullptr, *d_bc_size_x = nullptr, *d_bc_dst_off = nullptr, *d_bc_dst_kind = nullptr;
+    int32_t *d_plane_first_reg = nullptr, *d_plane_surf_offset = nullptr;
+    double *d_vol = nullptr, *d_exp = nullptr;
+    double *d_xstr = nullptr, *d_xstr_src = nullptr, *d_xs_self = nullptr, *d_src = nullptr, *d_flux = nullptr,
+           *d_qbar = nullptr, *d_tally = nullptr;
+    double *d_bc[2]   = {nullptr, nullptr};
+    int bc_cur        = 0;
+    double *d_current = nullptr, *d_surfflux = nullptr;
+    double *d_stage   = nullptr; // staging for column <-> [n][GP] transposes
+    size_t stage_elems = 0;
+    double *h_stage    = nullptr; // pinned
+    uint32_t *d_counters = nullptr;
+    int n_counters       = 0;
+    std::vector<WorkList> lists;
+    std::vector<bool> have_xs;
+    // streams / events
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    // stats
+    mocb200_stats stats{};
+    std::string error;
+};
+
+namespace {
+
+int fail(mocb200_sweeper *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h)
+        h->error = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(h, MOCB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                          \
+    } while (0)
+
+template <class T> int dev_alloc(mocb200_sweeper *h, T **out, size_t count)
+{
+    void *p      = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CUDA_TRY(h, cudaMalloc(&p, bytes));
+    h->allocs.push_back(p);
+    h->device_bytes += (int64_t)bytes;
+    *out = (T *)p;
+    return MOCB200_OK;
+}
+
+template <class T> int dev_upload(mocb200_sweeper *h, T **out, const T *src, size_t count)
+{
+    int rc = dev_alloc(h, out, count);
+    if (rc)
+        return rc;
+    if (count)
+        CUDA_TRY(h, cudaMemcpy(*out, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return MOCB200_OK;
+}
+
+template <class T> int dev_upload(mocb200_sweeper *h, T **out, const std::vector<T> &v)
+{
+    return dev_upload(h, out, v.data(), v.size());
+}
+
+int grid_for(int64_t n, int block, int sm_count)
+{
+    int64_t g = (n + block - 1) / block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm_count * 8));
+}
+
+// Unroll moc::Current::post_ray (moc_current_worker.hpp:202-264) for one track into the
+// list of coarse-surface crossings met in walk order, forward and backward.
+void build_crossings(const mocb200_problem &p, int64_t t, int nseg, std::vector<Cross> &fw, std::vector<Cross> &bw)
+{
+    auto normal_of_local = [&](int s) { return s < p.nx * p.ny + (p.nx + 1) * p.ny ? 0 : 1; };
+    int cell_fw = p.trk_cm_start[4 * t + 0], cell_bw = p.trk_cm_start[4 * t + 1];
+    int surf_fw = p.trk_cm_start[4 * t + 2], surf_bw = p.trk_cm_start[4 * t + 3];
+    int iseg_fw = 0, iseg_bw = nseg;
+    fw.push_back(Cross{iseg_fw, (surf_fw << 1) | normal_of_local(surf_fw)});
+    bw.push_back(Cross{nseg - iseg_bw, (surf_bw << 1) | normal_of_local(surf_bw)});
+    for (int64_t k = p.trk_cm_begin[t]; k < p.trk_cm_begin[t + 1]; k++) {
+        uint32_t c = p.cm_data[k];
+        int s_fw = c & 0xF, s_bw = (c >> 4) & 0xF, n_fw = (c >> 8) & 0xFF, n_bw = (c >> 16) & 0xFF;
+        if (s_fw != 7) { // Surface::INVALID
+            iseg_fw += n_fw;
+            int surf = p.coarse_surf[4 * cell_fw + s_fw];
+            fw.push_back(Cross{iseg_fw, (surf << 1) | ((s_fw == 0 || s_fw == 2) ? 0 : 1)});
+        }
+        if (s_bw != 7) {
+            iseg_bw -= n_bw;
+            int surf = p.coarse_surf[4 * cell_bw + s_bw];
+            bw.push_back(Cross{nseg - iseg_bw, (surf << 1) | ((s_bw == 0 || s_bw == 2) ? 0 : 1)});
+        }
+        if (s_fw < 4) {
+            int nb  = p.coarse_nbr[4 * cell_fw + s_fw];
+            cell_fw = nb < 0 ? cell_fw : nb;
+        }
+        if (s_bw < 4) {
+            int nb  = p.coarse_nbr[4 * cell_bw + s_bw];
+            cell_bw = nb < 0 ? cell_bw : nb;
+        }
+    }
+}
+
+int validate(const mocb200_problem *p)
+{
+    if (!p)
+        return fail(nullptr, MOCB200_ERR_INVALID, "problem is NULL");
+    if (p->n_group < 1 || p->n_reg < 1 || p->n_plane < 1 || p->n_unique < 1 || p->n_ang < 2 || p->n_geom < 1 ||
+        p->bc_per_group < 1 || p->exp_n < 1 || p->n_ang != 2 * p->ndir_oct)
+        return fail(nullptr, MOCB200_ERR_INVALID, "inconsistent problem dimensions");
+    if (p->n_seg >= (int64_t)INT32_MAX || p->n_cm >= (int64_t)INT32_MAX / 2)
+        return fail(nullptr, MOCB200_ERR_INVALID, "segment count exceeds 32-bit indexing (%lld)", (long long)p->n_seg);
+    const void *req[] = {p->ang_geom, p->ang_rsintheta, p->wt_v_st, p->cur_wx, p->cur_wy, p->flx_wx, p->flx_wy,
+                         p->bc_offset, p->bc_size_x, p->bc_size_y, p->bc_dst_off, p->bc_dst_kind,
+                         p->geom_trk_begin, p->trk_seg_begin, p->trk_bc, p->trk_cm_begin, p->trk_cm_start,
+                         p->seg_len, p->seg_fsr, p->cm_data, p->plane_unique, p->plane_first_reg,
+                         p->plane_cell_offset, p->plane_surf_offset, p->coarse_surf, p->coarse_nbr, p->vol,
+                         p->exp_table};
+    for (const void *q : req)
+        if (!q)
+            return fail(nullptr, MOCB200_ERR_INVALID, "problem has a NULL array");
+    for (int a = 0; a < p->n_ang; a++)
+        if (p->ang_geom[a] < 0 || p->ang_geom[a] >= p->n_geom)
+            return fail(nullptr, MOCB200_ERR_INVALID, "ang_geom out of range");
+    for (int ip = 0; ip < p->n_plane; ip++)
+        if (p->plane_unique[ip] < 0 || p->plane_unique[ip] >= p->n_unique)
+            return fail(nullptr, MOCB200_ERR_INVALID, "plane_unique out of range");
+    return MOCB200_OK;
+}
+
+int build(mocb200_sweeper *h, const mocb200_problem &p)
+{
+    const mocb200_options &opt = h->opt;
+    h->G = p.n_group;
+    h->GP = p.n_group <= 2 ? p.n_group : ((p.n_group + 3) & ~3);
+    h->n_reg = p.n_reg, h->n_plane = p.n_plane, h->n_ang = p.n_ang, h->bcpg = p.bc_per_group;
+    h->n_surf = p.n_surf, h->n_surf_plane = p.n_surf_plane;
+    h->exp_n = p.exp_n, h->exp_min = p.exp_min, h->exp_max = p.exp_max;
+    h->plane_begin = opt.plane_begin, h->plane_end = opt.plane_end;
+    if (h->plane_begin == 0 && h->plane_end == 0)
+        h->plane_end = p.n_plane;
+    if (h->plane_begin < 0 || h->plane_end > p.n_plane || h->plane_begin >= h->plane_end)
+        return fail(h, MOCB200_ERR_INVALID, "bad plane range [%d, %d)", h->plane_begin, h->plane_end);
+    int max_polar = opt.max_polar <= 0 ? 2 : std::min<int>(opt.max_polar, kMaxPolar);
+
+    // FSR range of this handle's planes (planes are stored contiguously, ascending)
+    h->reg_lo = p.plane_first_reg[h->plane_begin];
+    h->reg_hi = (h->plane_end < p.n_plane) ? p.plane_first_reg[h->plane_end] : p.n_reg;
+
+    // ---- polar bundles: angles of one octant that share a geometry ----
+    std::vector<Bundle> bundles;
+    std::vector<int> bundle_phase, bundle_geom;
+    for (int oct = 0; oct < 2; oct++) {
+        for (int geom = 0; geom < p.n_geom; geom++) {
+            std::vector<int> angs;
+            for (int a = oct * p.ndir_oct; a < (oct + 1) * p.ndir_oct; a++)
+                if (p.ang_geom[a] == geom)
+                    angs.push_back(a);
+            if (angs.empty())
+                continue;
+            int nchunk = ((int)angs.size() + max_polar - 1) / max_polar;
+            for (int c = 0; c < nchunk; c++) {
+                int lo = (int)((int64_t)angs.size() * c / nchunk), hi = (int)((int64_t)angs.size() * (c + 1) / nchunk);
+                Bundle b{};
+                b.np = hi - lo;
+                for (int i = lo; i < hi; i++)
+                    b.ang[i - lo] = angs[i];
+                for (int i = b.np; i < kMaxPolar; i++)
+                    b.ang[i] = angs[lo];
+                bundles.push_back(b);
+                bundle_phase.push_back(oct);
+                bundle_geom.push_back(geom);
+            }
+        }
+    }
+
+    // ---- crossing lists, one pair per track ----
+    std::vector<Cross> cross;
+    std::vector<int32_t> cross_begin_fw(p.n_trk), cross_n_fw(p.n_trk), cross_begin_bw(p.n_trk), cross_n_bw(p.n_trk);
+    {
+        std::vector<Cross> fw, bw;
+        for (int64_t t = 0; t < p.n_trk; t++) {
+            fw.clear();
+            bw.clear();
+            int nseg = (int)(p.trk_seg_begin[t + 1] - p.trk_seg_begin[t]);
+            build_crossings(p, t, nseg, fw, bw);
+            cross_begin_fw[t] = (int32_t)cross.size();
+            cross_n_fw[t]     = (int32_t)fw.size();
+            cross.insert(cross.end(), fw.begin(), fw.end());
+            cross_begin_bw[t] = (int32_t)cross.size();
+            cross_n_bw[t]     = (int32_t)bw.size();
+            cross.insert(cross.end(), bw.begin(), bw.end());
+        }
+    }
+
+    // ---- work lists ----
+    const bool jacobi = opt.boundary_update == MOCB200_BOUNDARY_JACOBI;
+    for (int u = 0; u < p.n_unique; u++) {
+        std::vector<int32_t> planes;
+        for (int ip = h->plane_begin; ip < h->plane_end; ip++)
+            if (p.plane_unique[ip] == u)
+                planes.push_back(ip);
+        if (planes.empty())
+            continue;
+        for (int phase = 0; phase < (jacobi ? 1 : 2); phase++) {
+            for (int np = 1; np <= kMaxPolar; np++) {
+                std::vector<Item> items;
+                for (size_t b = 0; b < bundles.size(); b++) {
+                    if (bundles[b].np != np || (!jacobi && bundle_phase[b] != phase))
+                        continue;
+                    int64_t t0 = p.geom_trk_begin[(size_t)u * p.n_geom + bundle_geom[b]];
+                    int64_t t1 = p.geom_trk_begin[(size_t)u * p.n_geom + bundle_geom[b] + 1];
+                    for (int64_t t = t0; t < t1; t++) {
+                        int64_t s0 = p.trk_seg_begin[t];
+                        int nseg   = (int)(p.trk_seg_begin[t + 1] - s0);
+                        Item f{(int32_t)s0, nseg, p.trk_bc[2 * t], p.trk_bc[2 * t + 1], (int32_t)b, 0,
+                               cross_begin_fw[t], cross_n_fw[t]};
+                        Item r{(int32_t)(s0 + nseg - 1), nseg, p.trk_bc[2 * t + 1], p.trk_bc[2 * t], (int32_t)b, 1,
+                               cross_begin_bw[t], cross_n_bw[t]};
+                        items.push_back(f);
+                        items.push_back(r);
+                    }
+                }
+                if (items.empty())
+                    continue;
+                // longest first: dynamic scheduling then behaves like LPT and warps stay homogeneous
+                std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) { return x.nseg > y.nseg; });
+                WorkList wl;
+                wl.unique = u, wl.phase = phase, wl.np = np;
+                wl.n_items  = (int32_t)items.size();
+                wl.n_planes = (int32_t)planes.size();
+                int64_t segs = 0;
+                for (const auto &it : items)
+                    segs += it.nseg;
+                wl.segs = segs * np * wl.n_planes;
+                if ((int64_t)wl.n_items * p.n_group * wl.n_planes >= (int64_t)UINT32_MAX - 64)
+                    return fail(h, MOCB200_ERR_INVALID, "work list too large for 32-bit scheduling");
+                int rc = dev_upload(h, &wl.d_items, items);
+                if (rc)
+                    return rc;
+                rc = dev_upload(h, &wl.d_planes, planes);
+                if (rc)
+                    return rc;
+                h->lists.push_back(wl);
+                h->stats.items[phase] += (int64_t)wl.n_items * wl.n_planes;
+            }
+        }
+    }
+    int64_t segs_ref = 0; // S: per-polar copies counted, both directions folded (= segs/2)
+    for (const auto &wl : h->lists)
+        segs_ref += wl.segs;
+    h->stats.segments_per_sweep = segs_ref / 2;
+    h->stats.unique_segments    = p.n_seg;
+
+    // ---- uploads ----
+    int rc;
+#define UP(dst, src, n)                                                                                      \
+    if ((rc = dev_upload(h, &(dst), (src), (size_t)(n))))                                                    \
+        return rc;
+    UP(h->d_seg_len, p.seg_len, p.n_seg);
+    UP(h->d_seg_fsr, p.seg_fsr, p.n_seg);
+    if ((rc = dev_upload(h, &h->d_cross, cross)))
+        return rc;
+    if ((rc = dev_upload(h, &h->d_bundles, bundles)))
+        return rc;
+    UP(h->d_rsin, p.ang_rsintheta, p.n_ang);
+    UP(h->d_wt, p.wt_v_st, (size_t)p.n_plane * p.n_ang);
+    {
+        std::vector<double> cw((size_t)p.n_plane * p.n_ang * 2), fw(cw.size());
+        for (size_t i = 0; i < (size_t)p.n_plane * p.n_ang; i++) {
+            cw[2 * i] = p.cur_wx[i], cw[2 * i + 1] = p.cur_wy[i];
+            fw[2 * i] = p.flx_wx[i], fw[2 * i + 1] = p.flx_wy[i];
+        }
+        if ((rc = dev_upload(h, &h->d_curw, cw)))
+            return rc;
+        if ((rc = dev_upload(h, &h->d_flxw, fw)))
+            return rc;
+    }
+    UP(h->d_bc_offset, p.bc_offset, 2 * p.n_ang);
+    UP(h->d_bc_size_x, p.bc_size_x, 2 * p.n_ang);
+    UP(h->d_bc_dst_off, p.bc_dst_off, 4 * p.n_ang);
+    UP(h->d_bc_dst_kind, p.bc_dst_kind, 4 * p.n_ang);
+    UP(h->d_plane_first_reg, p.plane_first_reg, p.n_plane);
+    UP(h->d_plane_surf_offset, p.plane_surf_offset, p.n_plane);
+    UP(h->d_vol, p.vol, p.n_reg);
+    UP(h->d_exp, p.exp_table, p.exp_n + 2);
+#undef UP
+
+    const size_t nrg = (size_t)p.n_reg * h->GP;
+    double **fsr_arrays[] = {&h->d_xstr, &h->d_xstr_src, &h->d_xs_self, &h->d_src, &h->d_flux, &h->d_qbar, &h->d_tally};
+    for (double **arr : fsr_arrays) {
+        if ((rc = dev_alloc(h, arr, nrg)))
+            return rc;
+        CUDA_TRY(h, cudaMemset(*arr, 0, nrg * sizeof(double)));
+    }
+    const size_t nbc = (size_t)p.n_plane * p.bc_per_group * h->GP;
+    for (int i = 0; i < (jacobi ? 2 : 1); i++) {
+        if ((rc = dev_alloc(h, &h->d_bc[i], nbc)))
+            return rc;
+        CUDA_TRY(h, cudaMemset(h->d_bc[i], 0, nbc * sizeof(double)));
+    }
+    if (!jacobi)
+        h->d_bc[1] = h->d_bc[0];
+    const size_t nsf = (size_t)p.n_surf * h->GP;
+    if ((rc = dev_alloc(h, &h->d_current, nsf)) || (rc = dev_alloc(h, &h->d_surfflux, nsf)))
+        return rc;
+    CUDA_TRY(h, cudaMemset(h->d_current, 0, nsf * sizeof(double)));
+    CUDA_TRY(h, cudaMemset(h->d_surfflux, 0, nsf * sizeof(double)));
+
+    h->stage_elems = std::max<size_t>({(size_t)p.n_reg, (size_t)p.bc_per_group, (size_t)p.n_surf}) * p.n_group;
+    if ((rc = dev_alloc(h, &h->d_stage, h->stage_elems)))
+        return rc;
+    CUDA_TRY(h, cudaMallocHost((void **)&h->h_stage, h->stage_elems * sizeof(double)));
+    h->n_counters = (int)h->lists.size();
+    if ((rc = dev_alloc(h, &h->d_counters, (size_t)h->n_counters)))
+        return rc;
+    h->have_xs.assign(p.n_group, false);
+    h->stats.device_bytes = h->device_bytes;
+    return MOCB200_OK;
+}
+
+typedef void (*SweepFn)(const SweepArgs);
+
+SweepFn pick_kernel(int np, int tally)
+{
+    switch (np * 2 + (tally ? 1 : 0)) {
+    case 2: return sweep_kernel<1, 0>;
+    case 3: return sweep_kernel<1, 1>;
+    case 4: return sweep_kernel<2, 0>;
+    case 5: return sweep_kernel<2, 1>;
+    case 6: return sweep_kernel<3, 0>;
+    case 7: return sweep_kernel<3, 1>;
+    case 8: return sweep_kernel<4, 0>;
+    case 9: return sweep_kernel<4, 1>;
+    }
+    return nullptr;
+}
+
+int check_groups(mocb200_sweeper *h, int g_begin, int g_count)
+{
+    if (!h)
+        return MOCB200_ERR_INVALID;
+    if (g_begin < 0 || g_count < 1 || g_begin + g_count > h->G)
+        return fail(h, MOCB200_ERR_INVALID, "group range [%d, %d) outside [0, %d)", g_begin, g_begin + g_count, h->G);
+    return MOCB200_OK;
+}
+
+// host columns [g_count][n] -> device [n][GP]
+int upload_columns(mocb200_sweeper *h, const double *host, int64_t n, int g_begin, int g_count, double *dst)
+{
+    const size_t elems = (size_t)n * g_count;
+    std::memcpy(h->h_stage, host, elems * sizeof(double));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, elems * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    scatter_columns_kernel<<<grid_for((int64_t)elems, 256, h->sm_count), 256, 0, h->stream>>>(n, h->GP, g_begin, g_count,
+                                                                                             h->d_stage, dst);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    // the pinned staging buffer is reused by the next call
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MOCB200_OK;
+}
+
+int download_columns(mocb200_sweeper *h, double *host, int64_t n, int g_begin, int g_count, const double *src)
+{
+    const size_t elems = (size_t)n * g_count;
+    gather_columns_kernel<<<grid_for((int64_t)elems, 256, h->sm_count), 256, 0, h->stream>>>(n, h->GP, g_begin, g_count,
+                                                                                            src, h->d_stage);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_stage, h->d_stage, elems * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(host, h->h_stage, elems * sizeof(double));
+    return MOCB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *mocb200_version(void)
+{
+    return "mocc_b200 0.1 (sm_100a)";
+}
+
+const char *mocb200_last_error(const mocb200_sweeper *h)
+{
+    return h ? h->error.c_str() : g_create_error.c_str();
+}
+
+int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb200_sweeper **out)
+{
+    if (!out)
+        return fail(nullptr, MOCB200_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = validate(prob);
+    if (rc)
+        return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, MOCB200_ERR_NO_DEVICE, "no CUDA device available (the MoC sweep has no CPU fallback)");
+    mocb200_sweeper *h = new mocb200_sweeper();
+    if (opt)
+        h->opt = *opt;
+    h->device = h->opt.device;
+    if (h->device < 0 || h->device >= ndev) {
+        const int bad = h->device;
+        delete h;
+        return fail(nullptr, MOCB200_ERR_INVALID, "device %d out of range (%d devices)", bad, ndev);
+    }
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess)
+        e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess)
+        e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (e != cudaSuccess) {
+        fail(nullptr, MOCB200_ERR_CUDA, "device set-up failed: %s", cudaGetErrorString(e));
+        delete h;
+        return MOCB200_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    rc = build(h, *prob);
+    if (rc) {
+        g_create_error = h->error;
+        mocb200_destroy(h);
+        return rc;
+    }
+    // opt in to the shared memory the table needs, for every kernel variant
+    const int smem = (h->exp_n + 2) * (int)sizeof(double);
+    for (int np = 1; np <= kMaxPolar; np++)
+        for (int t = 0; t < 2; t++) {
+            e = cudaFuncSetAttribute((const void *)pick_kernel(np, t), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) {
+                fail(nullptr, MOCB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+                mocb200_destroy(h);
+                return MOCB200_ERR_CUDA;
+            }
+        }
+    *out = h;
+    return MOCB200_OK;
+}
+
+int mocb200_destroy(mocb200_sweeper *h)
+{
+    if (!h)
+        return MOCB200_OK;
+    cudaSetDevice(h->device);
+    if (h->own_stream)
+        cudaStreamSynchronize(h->own_stream);
+    for (void *p : h->allocs)
+        cudaFree(p);
+    if (h->h_stage)
+        cudaFreeHost(h->h_stage);
+    if (h->ev0)
+        cudaEventDestroy(h->ev0);
+    if (h->ev1)
+        cudaEventDestroy(h->ev1);
+    if (h->own_stream)
+        cudaStreamDestroy(h->own_stream);
+    delete h;
+    return MOCB200_OK;
+}
+
+int mocb200_set_stream(mocb200_sweeper *h, void *cuda_stream)
+{
+    if (!h)
+        return MOCB200_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return MOCB200_OK;
+}
+
+int mocb200_synchronize(mocb200_sweeper *h)
+{
+    if (!h)
+        return MOCB200_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MOCB200_OK;
+}
+
+int mocb200_set_xs(mocb200_sweeper *h, int g_begin, int g_count, const double *xstr, const double *xstr_src,
+                   const double *xs_self)
+{
+    int rc = check_groups(h, g_begin, g_count);
+    if (rc)
+        return rc;
+    if (!xstr || !xs_self)
+        return fail(h, MOCB200_ERR_INVALID, "xstr and xs_self are required");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if ((rc = upload_columns(h, xstr, h->n_reg, g_begin, g_count, h->d_xstr)))
+        return rc;
+    if ((rc = upload_columns(h, xstr_src ? xstr_src : xstr, h->n_reg, g_begin, g_count, h->d_xstr_src)))
+        return rc;
+    if ((rc = upload_columns(h, xs_self, h->n_reg, g_begin, g_count, h->d_xs_self)))
+        return rc;
+    for (int g = g_begin; g < g_begin + g_count; g++)
+        h->have_xs[g] = true;
+    return MOCB200_OK;
+}
+
+#define COLUMN_SETTER(NAME, FIELD)                                                                           \
+    int NAME(mocb200_sweeper *h, int g_begin, int g_count, const double *v)                                  \
+    {                                                                                                        \
+        int rc = check_groups(h, g_begin, g_count);                                                          \
+        if (rc)                                                                                              \
+            return rc;                                                                                       \
+        if (!v)                                                                                              \
+            return fail(h, MOCB200_ERR_INVALID, #NAME ": NULL array");                                       \
+        CUDA_TRY(h, cudaSetDevice(h->device));                                                               \
+        return upload_columns(h, v, h->n_reg, g_begin, g_count, h->FIELD);                                   \
+    }
+COLUMN_SETTER(mocb200_set_source, d_src)
+COLUMN_SETTER(mocb200_set_flux, d_flux)
+COLUMN_SETTER(mocb200_set_qbar, d_qbar)
+#undef COLUMN_SETTER
+
+int mocb200_get_flux(mocb200_sweeper *h, int g_begin, int g_count, double *flux)
+{
+    int rc = check_groups(h, g_begin, g_count);
+    if (rc)
+        return rc;
+    if (!flux)
+        return fail(h, MOCB200_ERR_INVALID, "get_flux: NULL array");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return download_columns(h, flux, h->n_reg, g_begin, g_count, h->d_flux);
+}
+
+int mocb200_set_boundary(mocb200_sweeper *h, int plane, int g_begin, int g_count, const double *bc)
+{
+    int rc = check_groups(h, g_begin, g_count);
+    if (rc)
+        return rc;
+    if (plane < 0 || plane >= h->n_plane || !bc)
+        return fail(h, MOCB200_ERR_INVALID, "set_boundary: bad plane %d or NULL array", plane);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t off = (size_t)plane * h->bcpg * h->GP;
+    if ((rc = upload_columns(h, bc, h->bcpg, g_begin, g_count, h->d_bc[0] + off)))
+        return rc;
+    if (h->d_bc[1] != h->d_bc[0]) // Jacobi: PRESCRIBED faces are never rewritten, keep both copies alike
+        rc = upload_columns(h, bc, h->bcpg, g_begin, g_count, h->d_bc[1] + off);
+    return rc;
+}
+
+int mocb200_get_boundary(mocb200_sweeper *h, int plane, int g_begin, int g_count, double *bc)
+{
+    int rc = check_groups(h, g_begin, g_count);
+    if (rc)
+        return rc;
+    if (plane < 0 || plane >= h->n_plane || !bc)
+        return fail(h, MOCB200_ERR_INVALID, "get_boundary: bad plane %d or NULL array", plane);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t off = (size_t)plane * h->bcpg * h->GP;
+    return download_columns(h, bc, h->bcpg, g_begin, g_count, h->d_bc[h->bc_cur] + off);
+}
+
+int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int tally_mode, int use_qbar)
+{
+    int rc = check_groups(h, g_begin, g_count);
+    if (rc)
+        return rc;
+    if (n_inner < 1)
+        return fail(h, MOCB200_ERR_INVALID, "n_inner must be >= 1");
+    if (tally_mode != MOCB200_TALLY_NONE && tally_mode != MOCB200_TALLY_CURRENT)
+        return fail(h, MOCB200_ERR_INVALID, "tally mode %d not available", tally_mode);
+    for (int g = g_begin; g < g_begin + g_count; g++)
+        if (!h->have_xs[g])
+            return fail(h, MOCB200_ERR_STATE, "mocb200_set_xs has not been called for group %d", g);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const bool jacobi = h->opt.boundary_update == MOCB200_BOUNDARY_JACOBI;
+    const int block   = h->opt.block_threads > 0 ? std::min(512, (h->opt.block_threads + 31) & ~31) : 512;
+    const int smem    = (h->exp_n + 2) * (int)sizeof(double);
+    const int64_t nrg = (int64_t)(h->reg_hi - h->reg_lo) * g_count;
+
+    for (int inner = 0; inner < n_inner; inner++) {
+        const bool last = inner == n_inner - 1;
+        const int tally = last ? tally_mode : MOCB200_TALLY_NONE;
+        // q-bar and tally reset (whole FSR range: cheap, keeps indexing simple)
+        self_scatter_kernel<<<grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
+            h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_qbar, h->d_tally,
+            use_qbar ? 0 : 1);
+        h->stats.kernel_launches++;
+        if (tally == MOCB200_TALLY_CURRENT) {
+            zero_groups_kernel<<<grid_for((int64_t)h->n_surf * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
+                h->n_surf, h->GP, g_begin, g_count, h->d_current);
+            zero_groups_kernel<<<grid_for((int64_t)h->n_surf * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
+                h->n_surf, h->GP, g_begin, g_count, h->d_surfflux);
+            h->stats.kernel_launches += 2;
+        }
+        CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * h->n_counters, h->stream));
+        if (last)
+            CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        const double *bc_in = h->d_bc[h->bc_cur];
+        double *bc_out      = jacobi ? h->d_bc[1 - h->bc_cur] : h->d_bc[h->bc_cur];
+        for (int phase = 0; phase < (jacobi ? 1 : 2); phase++) {
+            for (size_t il = 0; il < h->lists.size(); il++) {
+                const WorkList &wl = h->lists[il];
+                if (wl.phase != phase)
+                    continue;
+                SweepArgs a{};
+                a.items = wl.d_items, a.n_items = wl.n_items, a.counter = h->d_counters + il;
+                a.bundles = h->d_bundles, a.planes = wl.d_planes, a.n_planes = wl.n_planes;
+                a.seg_len = h->d_seg_len, a.seg_fsr = h->d_seg_fsr, a.cross = h->d_cross;
+                a.ang_rsintheta = h->d_rsin, a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
+                a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
+                a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
+                a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
+                a.n_ang = h->n_ang, a.bc_per_group = h->bcpg;
+                a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP;
+                a.xstr = h->d_xstr, a.qbar = h->d_qbar, a.tally = h->d_tally;
+                a.bc_in = bc_in, a.bc_out = bc_out;
+                a.current = h->d_current, a.surface_flux = h->d_surfflux;
+                a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
+                const int64_t threads = (int64_t)wl.n_items * wl.n_planes * g_count;
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((threads + block - 1) / block,
+                                                                            (int64_t)h->sm_count * 2));
+                pick_kernel(wl.np, tally)<<<grid, block, smem, h->stream>>>(a);
+                h->stats.kernel_launches++;
+                h->stats.sweep_launches++;
+            }
+        }
+        if (last) {
+            CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+            h->ev_valid = true;
+        }
+        if (jacobi)
+            h->bc_cur = 1 - h->bc_cur;
+        finalize_flux_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
+            h->n_reg, h->GP, g_begin, g_count, h->d_tally, h->d_xstr, h->d_vol, h->d_qbar, h->d_flux, nullptr, h->reg_lo,
+            h->reg_hi);
+        h->stats.kernel_launches++;
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    return MOCB200_OK;
+}
+
+int mocb200_get_coarse(mocb200_sweeper *h, int group, double *current, double *surface_flux)
+{
+    int rc = check_groups(h, group, 1);
+    if (rc)
+        return rc;
+    if (!current || !surface_flux)
+        return fail(h, MOCB200_ERR_INVALID, "get_coarse: NULL array");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if ((rc = download_columns(h, current, h->n_surf, group, 1, h->d_current)))
+        return rc;
+    return download_columns(h, surface_flux, h->n_surf, group, 1, h->d_surfflux);
+}
+
+int mocb200_get_stats(const mocb200_sweeper *h, mocb200_stats *out)
+{
+    if (!h || !out)
+        return MOCB200_ERR_INVALID;
+    *out = h->stats;
+    return MOCB200_OK;
+}
+
+int mocb200_last_sweep_ms(mocb200_sweeper *h, double *ms)
+{
+    if (!h || !ms)
+        return MOCB200_ERR_INVALID;
+    if (!h->ev_valid)
+        return fail(h, MOCB200_ERR_STATE, "no sweep has been timed yet");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+    float f = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    *ms = f;
+    return MOCB200_OK;
+}
+
+} // extern "C"

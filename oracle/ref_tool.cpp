@@ -1,0 +1,395 @@
+// ref_tool.cpp -- TEST INFRASTRUCTURE ONLY (oracle side).
+//
+// Links the UNMODIFIED reference (oracle/_ref/libmocc_ref.a) and
+//   flat    <in.xml> <out.mocflat>              flatten the reference's ray data
+//   golden  <in.xml> <out_prefix>               flat file + per-sweep1g records produced by the
+//                                               reference kernel (moc_sweeper_kernel.inc.hpp:36-180)
+//   solve   <in.xml> <out.golden>               run the reference solver unchanged; dump k, flux
+//   time    <in.xml> [--sweeps N]               time the reference CPU sweep (JSON to stdout)
+// Options (any command):
+//   --set path/to/node@attr=value               amend the XML before it is parsed
+//   --outers N  --records "o:g:i,o:g:i,..."     (golden) outer iterations; which sweeps to record
+//   --cmfd                                      (golden) attach a CoarseData so that the last
+//                                               inner runs moc::Current
+// Nothing in the product path (mocc_b200/) calls into this file.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <omp.h>
+
+#include "pugixml.hpp"
+
+#include "core/coarse_data.hpp"
+#include "core/core_mesh.hpp"
+#include "core/source.hpp"
+#include "solvers/eigen_solver.hpp"
+#include "solvers/solver_factory.hpp"
+#include "sweepers/moc/moc_current_worker.hpp"
+#include "sweepers/moc/moc_sweeper.hpp"
+#include "util/files.hpp"
+
+#include "arrayfile.hpp"
+#include "flatten.hpp"
+
+using namespace mocc;
+using mocc_b200::ArrayFile;
+
+namespace {
+
+struct RecordKey {
+    int outer, group, inner;
+    bool operator<(const RecordKey &o) const
+    {
+        return std::tie(outer, group, inner) < std::tie(o.outer, o.group, o.inner);
+    }
+};
+
+// Gives the tool access to MoCSweeper's protected state and to the reference
+// kernel sweep1g<>. sweep_recorded() follows MoCSweeper::sweep
+// (moc_sweeper.cpp:189-225) step by step so that inputs and outputs of every
+// sweep1g call can be captured.
+class ExposedMoC : public moc::MoCSweeper {
+public:
+    ExposedMoC(const pugi::xml_node &input, const CoreMesh &mesh) : moc::MoCSweeper(input, mesh)
+    {
+    }
+
+    mocc_b200::FlatProblem flat() const
+    {
+        std::vector<double> vol(vol_.begin(), vol_.end());
+        return mocc_b200::flatten(mesh_, rays_, macroplane_unique_ids_, first_reg_macroplane_,
+                                  vol.data(), (int)n_reg_, (int)n_group_);
+    }
+    Source *source()
+    {
+        return source_;
+    }
+    int n_inner() const
+    {
+        return n_inner_;
+    }
+    bool gs() const
+    {
+        return gauss_seidel_boundary_;
+    }
+    int bc_per_group() const
+    {
+        return boundary_[0].size() / n_group_;
+    }
+    std::vector<double> bc_in(int group) const
+    {
+        std::vector<double> out;
+        int n = bc_per_group();
+        for (const auto &b : boundary_) {
+            const real_t *p = b.get_boundary(group, 0).second;
+            out.insert(out.end(), p, p + n);
+        }
+        return out;
+    }
+    std::vector<double> xs_per_reg(int group, int which) const
+    {
+        std::vector<double> out(n_reg_);
+        for (const auto &xsr : *xs_mesh_) {
+            double v = 0.0;
+            switch (which) {
+            case 0:
+                v = xsr.xsmactr(group);
+                break;
+            case 1:
+                v = xsr.xsmacsc().to(group)[group];
+                break;
+            case 2:
+                v = xsr.xsmacnf(group);
+                break;
+            case 3:
+                v = xsr.xsmacch(group);
+                break;
+            }
+            for (const int ireg : xsr.reg())
+                out[ireg] = v;
+        }
+        return out;
+    }
+    // scattering matrix expanded to FSRs: out[gfrom][ireg] for scattering INTO `group`
+    std::vector<double> xs_scat_to(int group) const
+    {
+        std::vector<double> out((size_t)n_group_ * n_reg_, 0.0);
+        for (const auto &xsr : *xs_mesh_) {
+            const ScatteringRow &row = xsr.xsmacsc().to(group);
+            for (int gf = row.min_g; gf <= row.max_g; gf++)
+                for (const int ireg : xsr.reg())
+                    out[(size_t)gf * n_reg_ + ireg] = row[gf];
+        }
+        return out;
+    }
+
+    void sweep_recorded(int group, int outer, const std::set<RecordKey> &want, ArrayFile &out, int &n_rec)
+    {
+        xstr_.expand(group, split_);
+        flux_1g_.reference(flux_(blitz::Range::all(), group));
+        for (unsigned int inner = 0; inner < n_inner_; inner++) {
+            bool rec = want.count(RecordKey{outer, group, (int)inner}) != 0;
+            std::string p = "rec" + std::to_string(n_rec) + "_";
+            if (rec) {
+                out.put_scalar<int32_t>(p + "outer", outer);
+                out.put_scalar<int32_t>(p + "group", group);
+                out.put_scalar<int32_t>(p + "inner", (int)inner);
+                std::vector<double> fin(flux_1g_.begin(), flux_1g_.end());
+                out.put(p + "flux_in", fin);
+                const VectorX &s = source_->get();
+                out.put(p + "src", s.data(), {(uint64_t)s.size()});
+                out.put(p + "bc_in", bc_in(group));
+            }
+            source_->self_scatter(group, xstr_.xs());
+            if (rec) {
+                const VectorX &q = source_->get_transport(0);
+                out.put(p + "qbar", q.data(), {(uint64_t)q.size()});
+                std::vector<double> x(xstr_.xs().begin(), xstr_.xs().end());
+                out.put(p + "xstr", x);
+            }
+            int mode = 0;
+            if (inner == n_inner_ - 1 && coarse_data_) {
+                coarse_data_->zero_data_radial(group);
+                moc::Current cw(coarse_data_, &mesh_);
+                this->sweep1g(group, cw);
+                coarse_data_->set_has_radial_data(true);
+                mode = 1;
+            } else {
+                moc::NoCurrent cw(coarse_data_, &mesh_);
+                this->sweep1g(group, cw);
+            }
+            if (rec) {
+                out.put_scalar<int32_t>(p + "mode", mode);
+                std::vector<double> fout(flux_1g_.begin(), flux_1g_.end());
+                out.put(p + "flux_out", fout);
+                out.put(p + "bc_out", bc_in(group));
+                if (mode == 1) {
+                    auto all = blitz::Range::all();
+                    auto c   = coarse_data_->current(all, group);
+                    auto sf  = coarse_data_->surface_flux(all, group);
+                    std::vector<double> cv(c.begin(), c.end()), sv(sf.begin(), sf.end());
+                    out.put(p + "current", cv);
+                    out.put(p + "surface_flux", sv);
+                }
+                n_rec++;
+            }
+        }
+    }
+};
+
+void set_xml(pugi::xml_document &doc, const std::string &spec)
+{
+    // path/to/node@attr=value
+    auto at = spec.find('@');
+    auto eq = spec.find('=', at);
+    if (at == std::string::npos || eq == std::string::npos)
+        throw std::runtime_error("bad --set spec: " + spec);
+    std::string path = spec.substr(0, at), attr = spec.substr(at + 1, eq - at - 1),
+                val = spec.substr(eq + 1);
+    pugi::xml_node node = doc;
+    std::stringstream ss(path);
+    std::string part;
+    while (std::getline(ss, part, '/')) {
+        pugi::xml_node c = node.child(part.c_str());
+        if (c.empty())
+            c = node.append_child(part.c_str());
+        node = c;
+    }
+    if (node.attribute(attr.c_str()).empty())
+        node.append_attribute(attr.c_str());
+    node.attribute(attr.c_str()).set_value(val.c_str());
+}
+
+std::set<RecordKey> parse_records(const std::string &s)
+{
+    std::set<RecordKey> out;
+    std::stringstream ss(s);
+    std::string item;
+    while (std::getline(ss, item, ',')) {
+        RecordKey k;
+        if (std::sscanf(item.c_str(), "%d:%d:%d", &k.outer, &k.group, &k.inner) != 3)
+            throw std::runtime_error("bad --records item: " + item);
+        out.insert(k);
+    }
+    return out;
+}
+
+double total_fission(const TransportSweeper &sw, bool old)
+{
+    return sw.total_fission(old);
+}
+}
+
+int main(int argc, char **argv)
+{
+    try {
+        if (argc < 3) {
+            std::cerr << "usage: ref_tool flat|golden|solve|time <in.xml> [out] [options]\n";
+            return 2;
+        }
+        std::string cmd = argv[1], xml = argv[2];
+        std::string out_path;
+        std::vector<std::string> sets;
+        int outers = 1, sweeps = 2;
+        bool cmfd  = false;
+        std::string records;
+        for (int i = 3; i < argc; i++) {
+            std::string a = argv[i];
+            if (a == "--set" && i + 1 < argc)
+                sets.push_back(argv[++i]);
+            else if (a == "--outers" && i + 1 < argc)
+                outers = std::atoi(argv[++i]);
+            else if (a == "--sweeps" && i + 1 < argc)
+                sweeps = std::atoi(argv[++i]);
+            else if (a == "--records" && i + 1 < argc)
+                records = argv[++i];
+            else if (a == "--cmfd")
+                cmfd = true;
+            else if (out_path.empty())
+                out_path = a;
+            else
+                throw std::runtime_error("unknown argument: " + a);
+        }
+
+        pugi::xml_document doc;
+        auto res = doc.load_file(xml.c_str());
+        if (!res)
+            throw std::runtime_error("cannot parse " + xml + ": " + res.description());
+        for (const auto &s : sets)
+            set_xml(doc, s);
+
+        StartLogFile("ref_tool");
+        RootTimer.tic();
+
+        if (cmd == "solve") {
+            CoreMesh mesh(doc);
+            auto solver = SolverFactory(doc.child("solver"), mesh);
+            auto t0     = std::chrono::steady_clock::now();
+            solver->solve();
+            double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const TransportSweeper *sw = solver->sweeper();
+            ArrayFile out;
+            const ArrayB2 &flux = sw->flux();
+            std::vector<double> f(flux.begin(), flux.end());
+            out.put("flux", f.data(), {(uint64_t)flux.extent(0), (uint64_t)flux.extent(1)});
+            // k is not exposed by the Solver interface: recompute the final update ratio is not
+            // possible either, so parse it from the convergence log the reference prints. The
+            // caller reads k from stdout; here we only store flux and timing.
+            out.put_scalar<double>("solve_seconds", secs);
+            ArrayB3 pp = sw->pin_powers();
+            std::vector<double> ppv(pp.begin(), pp.end());
+            out.put("pin_powers", ppv);
+            if (!out_path.empty())
+                out.save(out_path);
+            RootTimer.toc();
+            std::cout << RootTimer << std::endl;
+            return 0;
+        }
+
+        CoreMesh mesh(doc);
+        pugi::xml_node solver_node = doc.child("solver");
+        ExposedMoC sw(solver_node.child("sweeper"), mesh);
+
+        if (cmd == "flat") {
+            sw.flat().to_arrayfile().save(out_path);
+            return 0;
+        }
+
+        UP_Source_t source = sw.create_source(solver_node.child("source"));
+        sw.assign_source(source.get());
+        std::unique_ptr<CoarseData> cd;
+        if (cmfd) {
+            cd.reset(new CoarseData(mesh, sw.n_group()));
+            sw.set_coarse_data(cd.get());
+        }
+        const int ng = sw.n_group();
+
+        if (cmd == "golden") {
+            auto fp = sw.flat();
+            fp.to_arrayfile().save(out_path + ".mocflat");
+            ArrayFile out;
+            out.put_scalar<int32_t>("n_inner", sw.n_inner());
+            out.put_scalar<int32_t>("gs_boundary", sw.gs() ? 1 : 0);
+            out.put_scalar<int32_t>("n_outer", outers);
+            for (int g = 0; g < ng; g++) {
+                out.put("xs_tr_" + std::to_string(g), sw.xs_per_reg(g, 0));
+                out.put("xs_self_" + std::to_string(g), sw.xs_per_reg(g, 1));
+                out.put("xs_nf_" + std::to_string(g), sw.xs_per_reg(g, 2));
+                out.put("xs_ch_" + std::to_string(g), sw.xs_per_reg(g, 3));
+                out.put("xs_scat_to_" + std::to_string(g), sw.xs_scat_to(g));
+            }
+            std::set<RecordKey> want = parse_records(records);
+            sw.initialize();
+            real_t k = 1.0;
+            ArrayB1 fs(sw.n_reg());
+            int n_rec = 0;
+            std::vector<double> khist;
+            for (int outer = 0; outer < outers; outer++) {
+                sw.calc_fission_source(k, fs);
+                sw.store_old_flux();
+                for (int ig = 0; ig < ng; ig++) {
+                    source->initialize_group(ig);
+                    source->fission(fs, ig);
+                    source->in_scatter(ig);
+                    sw.sweep_recorded(ig, outer, want, out, n_rec);
+                }
+                k = k * total_fission(sw, false) / total_fission(sw, true);
+                khist.push_back(k);
+            }
+            out.put_scalar<int32_t>("n_rec", n_rec);
+            out.put("k_history", khist);
+            const ArrayB2 &flux = sw.flux();
+            std::vector<double> f(flux.begin(), flux.end());
+            out.put("flux_final", f.data(), {(uint64_t)flux.extent(0), (uint64_t)flux.extent(1)});
+            out.save(out_path + ".golden");
+            std::printf("golden: %d records, k after %d outers = %.12f\n", n_rec, outers, (double)k);
+            return 0;
+        }
+
+        if (cmd == "time") {
+            // Time `sweeps` full passes (every group once, n_inner inners each) of the
+            // reference sweeper, after one untimed warm-up pass.
+            auto fp         = sw.flat();
+            int64_t S       = fp.n_seg_reference;
+            sw.initialize();
+            ArrayB1 fs(sw.n_reg());
+            sw.calc_fission_source(1.0, fs);
+            auto pass = [&]() {
+                for (int ig = 0; ig < ng; ig++) {
+                    source->initialize_group(ig);
+                    source->fission(fs, ig);
+                    source->in_scatter(ig);
+                    sw.sweep(ig);
+                }
+            };
+            pass();
+            auto t0 = std::chrono::steady_clock::now();
+            for (int i = 0; i < sweeps; i++)
+                pass();
+            double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            double updates = 2.0 * (double)S * ng * sw.n_inner() * sweeps;
+            std::printf("{\"impl\": \"reference\", \"segments\": %lld, \"groups\": %d, \"n_inner\": %d, "
+                        "\"passes\": %d, \"updates\": %.0f, \"seconds\": %.6f, \"updates_per_s\": %.6e, "
+                        "\"threads\": %d, \"current_tally\": %s}\n",
+                        (long long)S, ng, sw.n_inner(), sweeps, updates, secs, updates / secs,
+                        omp_get_max_threads(), cmfd ? "true" : "false");
+            return 0;
+        }
+        throw std::runtime_error("unknown command: " + cmd);
+    } catch (const mocc::Exception &e) {
+        std::cerr << "ref_tool: reference exception: " << e.what() << std::endl;
+        return 1;
+    } catch (const std::exception &e) {
+        std::cerr << "ref_tool: " << e.what() << std::endl;
+        return 1;
+    }
+}

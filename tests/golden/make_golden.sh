@@ -1,0 +1,33 @@
+#!/bin/bash
+# Regenerates the golden fixtures in this directory by running the UNMODIFIED
+# reference (oracle/_ref/ref_tool, built by `make -C oracle ref` from the sources
+# under /root/reference). Single-threaded so that reductions are deterministic.
+#   *.mocflat.gz  flattened ray data of the case (mocc_b200/host/flatten.cpp)
+#   *.golden.gz   inputs/outputs of selected reference sweep1g calls + k history
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+TOOL="$ROOT/oracle/_ref/ref_tool"
+WORK="$(mktemp -d)"
+trap 'rm -rf "$WORK"' EXIT
+cp "$HERE"/inputs/* "$WORK"/
+cp "$ROOT"/oracle/_ref/inputs/3x3.xml "$ROOT"/oracle/_ref/inputs/c5g7.xsl "$WORK"/
+cd "$WORK"
+export OMP_NUM_THREADS=1
+
+run() { # name xml records [extra args...]
+    local name="$1" xml="$2" rec="$3"; shift 3
+    "$TOOL" golden "$xml" "$WORK/$name" --outers 2 --records "$rec" "$@" > "$WORK/$name.log" 2>&1 \
+        || { tail -20 "$WORK/$name.log"; exit 1; }
+    tail -1 "$WORK/$name.log"
+    # geometry shared with mini2d_gs is stored once
+    case "$name" in mini2d_jacobi|mini2d_nocmfd) ;; *) gzip -9 -n -c "$WORK/$name.mocflat" > "$HERE/$name.mocflat.gz";; esac
+    gzip -9 -n -c "$WORK/$name.golden" > "$HERE/$name.golden.gz"
+}
+
+run mini2d_gs     mini2d.xml "0:0:0,0:1:2,1:2:2,1:0:1" --cmfd
+run mini2d_jacobi mini2d.xml "0:0:0,0:1:2,1:2:2" --cmfd --set solver/sweeper@boundary_update=jacobi
+run mini2d_nocmfd mini2d.xml "0:0:2,1:1:2"
+run mini3d_gs     mini3d.xml "0:0:0,0:1:1,1:2:1" --cmfd
+run 3x3_s05_gs    3x3.xml    "0:0:0,0:3:4,1:6:4" --cmfd --set solver/sweeper/rays@spacing=0.05
+ls -la "$HERE"/*.gz

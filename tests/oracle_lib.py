@@ -1,0 +1,65 @@
+"""ctypes access to the CPU oracle (oracle/libmoc_oracle.so). TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from mocc_b200.capi import Problem, problem_from_arrays
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "libmoc_oracle.so")
+_f64p = C.POINTER(C.c_double)
+
+_lib = None
+
+
+def oracle():
+    global _lib
+    if _lib is None:
+        src = os.path.join(ORACLE_DIR, "moc_oracle.c")
+        if (not os.path.exists(ORACLE_LIB)) or os.path.getmtime(ORACLE_LIB) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "c"], stdout=subprocess.DEVNULL)
+        lib = C.CDLL(ORACLE_LIB)
+        lib.moc_oracle_exp.argtypes = [_f64p, C.c_int, C.c_double, C.c_double, C.c_double]
+        lib.moc_oracle_exp.restype = C.c_double
+        lib.moc_oracle_self_scatter.argtypes = [C.c_int] + [_f64p] * 5
+        lib.moc_oracle_self_scatter.restype = None
+        lib.moc_oracle_sweep1g.argtypes = [C.POINTER(Problem), C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p,
+                                           _f64p, _f64p, _f64p]
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_f64p)
+
+
+def oracle_exp(table, v, n=10000, vmin=-10.0, vmax=0.0):
+    t = np.ascontiguousarray(table, dtype=np.float64)
+    return oracle().moc_oracle_exp(_p(t), n, vmin, vmax, float(v))
+
+
+def oracle_self_scatter(src, flux, xs_self, xs_tr):
+    src, flux, xs_self, xs_tr = (np.ascontiguousarray(x, dtype=np.float64) for x in (src, flux, xs_self, xs_tr))
+    q = np.empty_like(src)
+    oracle().moc_oracle_self_scatter(src.size, _p(src), _p(flux), _p(xs_self), _p(xs_tr), _p(q))
+    return q
+
+
+def oracle_sweep1g(arrays, xstr, qbar, bc_in, gs_boundary=True, tally_mode=0):
+    """Returns (flux_out, bc_after, current, surface_flux); bc_in is [n_plane, bc_per_group]."""
+    prob, keep = problem_from_arrays(arrays)
+    xstr = np.ascontiguousarray(xstr, dtype=np.float64)
+    qbar = np.ascontiguousarray(qbar, dtype=np.float64)
+    bc = np.array(bc_in, dtype=np.float64, copy=True).reshape(prob.n_plane, prob.bc_per_group)
+    flux = np.zeros(prob.n_reg)
+    cur = np.zeros(prob.n_surf)
+    sf = np.zeros(prob.n_surf)
+    area = np.ascontiguousarray(arrays["surf_area"], dtype=np.float64)
+    rc = oracle().moc_oracle_sweep1g(C.byref(prob), int(gs_boundary), tally_mode, _p(xstr), _p(qbar), _p(bc),
+                                     _p(flux), _p(cur), _p(sf), _p(area))
+    if rc != 0:
+        raise RuntimeError("oracle sweep failed")
+    return flux, bc, cur, sf
