@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the MoC transport sweep on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode pergroup|batched] [--impl reference]
+
+Workload (config.workload): C5G7 2-D, `examples/c5g7_2d.xml` as shipped by the reference
+(7 groups, Chebyshev-Gauss 8x2 per octant, ray spacing 0.05 cm, n_inner = 10, CMFD on so the
+last inner of every group tallies coarse currents). One STEP is what
+FixedSourceSolver::step asks of the sweeper (src/solvers/fixed_source_solver.cpp:102-117):
+sweep(g) for every group g, each n_inner inner iterations = 2*S*G*n_inner segment-group
+updates (S = reference segment count, polar copies counted).
+
+  value   device-resident: sources/XS/boundary flux already in HBM, only sweeps are timed
+  e2e     the same step through the C ABI with HOST buffers: per group the one-group source,
+          scalar flux and boundary flux go host->device and flux, boundary flux and coarse
+          tallies come back, exactly what the C++ plugin (mocc_b200/host) does per sweep(group)
+  mode    pergroup: one mocb200_sweep per group (the reference's sweep(group) contract,
+          Gauss-Seidel in energy); batched: all groups in one mocb200_sweep (8 group lanes)
+
+With N > 1 (torchrun, one rank per GPU) every rank owns one axial plane of an N-plane stack
+of C5G7 planes -- the plane sharding the 2D3D method uses; planes are independent inside a
+sweep, so there is no data-path collective (scaling "weak").
+
+--impl reference times the UNMODIFIED reference CPU sweeper (oracle/_ref/ref_tool, OpenMP on
+all host cores) on the same input; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MoC segment-group updates/s per sweep"
+UNIT = "updates/s"
+BYTES_PER_UPDATE = 6.10  # SURVEY.md 8(d) contract figure, per-group sweep of C5G7-2D (reference layout)
+BIN = os.path.join(ROOT, "mocc_b200", "bin")
+REF_TOOL = os.path.join(ROOT, "oracle", "_ref", "ref_tool")
+CACHE = os.environ.get("MOCC_B200_CACHE", "/tmp/mocc_b200_bench")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_files():
+    """Flatten examples/c5g7_2d.xml with the plugin's own setup code (mocc_flatten)."""
+    os.makedirs(CACHE, exist_ok=True)
+    flat = os.path.join(CACHE, "c5g7_2d.mocflat")
+    if not os.path.exists(flat):
+        tool = os.path.join(BIN, "mocc_flatten")
+        inputs = os.path.join(BIN, "inputs")
+        if not os.path.exists(tool):
+            raise RuntimeError("mocc_b200/bin/mocc_flatten missing: run __graft_entry__.build() where the "
+                               "reference sources are available")
+        tmp = flat + f".tmp{os.getpid()}"
+        subprocess.check_call([tool, "c5g7_2d.xml", tmp, "--xs"], cwd=inputs, stdout=subprocess.DEVNULL)
+        os.replace(tmp, flat)
+    return flat
+
+
+def synthetic_source(arr, G, n_reg):
+    """Fixed one-group sources from a flat unit flux: fission (k = 1) + in-scatter; synthetic."""
+    nf, ch, scat = arr["xs_nf"], arr["xs_ch"], arr["xs_scat"]
+    fis = nf.sum(axis=0)  # sum_g nu-fission * flux(=1)
+    src = np.empty((G, n_reg))
+    for g in range(G):
+        inscat = scat[g].sum(axis=0) - scat[g, g]
+        src[g] = ch[g] * fis + inscat
+    return src
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], 0.0, set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = max(smax, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        busy = [x for x in sm if x > 0.5 * smax] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """The reference's own CPU sweep (unmodified sources, oracle/_ref) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    if not os.path.exists(REF_TOOL):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_tool not built"}))
+        return
+    total = args.steps + args.warmup
+    n_inner = max(1, min(10, 30 // max(total, 1)))
+    inputs = os.path.join(ROOT, "oracle", "_ref", "inputs")
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+    cmd = [REF_TOOL, "time", "c5g7_2d.xml", "--cmfd", "--sweeps", str(args.steps), "--warmup", str(args.warmup),
+           "--set", f"solver/sweeper@n_inner={n_inner}"]
+    out = subprocess.run(cmd, cwd=inputs, env=env, capture_output=True, text=True, check=True).stdout
+    res = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+    value = res["updates_per_s"]
+    sample = (f"{args.steps} passes of c5g7_2d.xml: 7 groups x {n_inner} inner sweeps each (last inner with the "
+              f"moc::Current tally), {res['updates']:.3e} updates in {res['seconds']:.2f} s")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "examples/c5g7_2d.xml geometry and cross sections, flat initial flux",
+        "config": {"workload": "C5G7 2-D (examples/c5g7_2d.xml), reference MoCSweeper on CPU", "n_inner": n_inner,
+                   "threads": res["threads"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="pergroup", choices=["pergroup", "batched"])
+    ap.add_argument("--boundary", default="gs", choices=["gs", "jacobi"])
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from mocc_b200 import Sweeper, load_arrays
+    from mocc_b200.capi import TALLY_CURRENT
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the MoC sweep has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if rank == 0:
+        flat_path = workload_files()
+    barrier()
+    flat_path = workload_files()
+    arr = load_arrays(flat_path)
+    G, n_reg, n_plane = (int(arr[k][0]) for k in ("n_group", "n_reg", "n_plane"))
+    S = int(arr["n_seg_reference"][0])
+    bcpg, n_surf = int(arr["bc_per_group"][0]), int(arr["n_surf"][0])
+    n_inner = int(arr["n_inner"][0])
+    gs = args.boundary == "gs"
+    src = synthetic_source(arr, G, n_reg)
+
+    sw = Sweeper(arr, device=local, boundary_update=0 if gs else 1, kernel=args.kernel)
+    # a dedicated non-default stream: the C ABI treats a NULL stream as "use the handle's own", and
+    # torch events only see work on the stream they are recorded on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sw.set_stream(stream.cuda_stream)
+    sw.set_xs(0, arr["xs_tr"], xstr_src=arr["xs_tr"], xs_self=arr["xs_self"])
+    sw.set_source(0, src)
+    sw.set_flux(0, np.ones((G, n_reg)))
+    bc0 = np.full((G, bcpg), 1.0 / (4.0 * np.pi))
+    for ip in range(n_plane):
+        sw.set_boundary(ip, 0, bc0)
+
+    def step_device():
+        if args.mode == "batched":
+            sw.sweep(0, G, n_inner=n_inner, tally_mode=TALLY_CURRENT)
+        else:
+            for g in range(G):
+                sw.sweep(g, 1, n_inner=n_inner, tally_mode=TALLY_CURRENT)
+
+    flux_h = np.ones((G, n_reg))
+    bc_h = [bc0.copy() for _ in range(n_plane)]
+    h2d = d2h = 0
+
+    def step_e2e(count=False):
+        nonlocal h2d, d2h
+        groups = [range(G)] if args.mode == "batched" else [[g] for g in range(G)]
+        for gl in groups:
+            for g in gl:
+                sw.set_source(g, src[g])
+                sw.set_flux(g, flux_h[g])
+                for ip in range(n_plane):
+                    sw.set_boundary(ip, g, bc_h[ip][g])
+            sw.sweep(gl[0], len(gl), n_inner=n_inner, tally_mode=TALLY_CURRENT)
+            for g in gl:
+                sw.get_flux(g, 1, out=flux_h[g:g + 1])
+                for ip in range(n_plane):
+                    bc_h[ip][g] = sw.get_boundary(ip, g, 1)[0]
+                sw.get_coarse(g)
+        if count:
+            h2d = G * 8 * (2 * n_reg + n_plane * bcpg)
+            d2h = G * 8 * (n_reg + n_plane * bcpg + 2 * n_surf)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = sw.stats()["kernel_launches"]
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in ev:
+        flush.zero_()  # evict the previous step's working set (untimed)
+        e0.record(stream)
+        step_device()
+        e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    launches = sw.stats()["kernel_launches"] - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    ln = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    updates_step = 2.0 * S * G * n_inner * world  # every rank sweeps its own plane
+    value = updates_step * args.steps / (ms * 1e-3)
+
+    # ---- dominant kernel: live CUDA-event time of the sweep kernels of one inner iteration ----
+    sw.set_timing(True)
+    flush.zero_()
+    step_device()
+    k_ms, k_n = sw.get_timing()
+    sw.set_timing(False)
+    sweep_ms = k_ms / max(k_n, 1)                 # one inner sweep of the group set of one call
+    groups_per_call = G if args.mode == "batched" else 1
+    upd_per_sweep = 2.0 * S * groups_per_call
+    peak, peak_src = peaks()
+    # contract figure: 6.10 B per update, reference layout, per-group sweep. The resident layout
+    # shares geometry between the polar copies; its own compulsory bytes are reported beside it.
+    n_useg = int(arr["seg_len"].size)
+    n_ray = int(arr["n_ray_reference"][0])
+    bytes_contract = BYTES_PER_UPDATE * 2.0 * S if args.mode == "pergroup" else \
+        12.0 * S + groups_per_call * (24.0 * n_reg + 32.0 * n_ray)
+    bytes_resident = 12.0 * n_useg + groups_per_call * (24.0 * n_reg + 32.0 * n_ray)
+    achieved = bytes_contract / (sweep_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.mode)
+
+    # ---- end to end through the C ABI with host buffers ----
+    step_e2e(count=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = updates_step * args.steps / float(t.item())
+
+    # ---- reference CPU sweep on this box's host cores (rank 0, N = 1): one step of the same workload ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_TOOL):
+        cores = os.cpu_count() or 1
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+        out = subprocess.run([REF_TOOL, "time", "c5g7_2d.xml", "--cmfd", "--sweeps", "1", "--warmup", "0"],
+                             cwd=os.path.join(ROOT, "oracle", "_ref", "inputs"), env=env, capture_output=True,
+                             text=True)
+        js = [x for x in out.stdout.splitlines() if x.startswith("{")]
+        if js:
+            r = json.loads(js[-1])
+            cpu = {"value": r["updates_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                   "sample": f"one step of the same workload (7 groups x {r['n_inner']} inners, moc::Current on the "
+                             f"last inner): {r['updates']:.3e} updates in {r['seconds']:.2f} s, reference MoCSweeper "
+                             f"(OpenMP, unmodified sources in oracle/_ref)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64",
+            "data": "examples/c5g7_2d.xml geometry and cross sections (flattened on the box); synthetic fixed "
+                    "source (fission + in-scatter of a flat unit flux)",
+            "config": {"workload": "C5G7 2-D (examples/c5g7_2d.xml): 7 groups, cg 8x2, spacing 0.05, n_inner 10, "
+                                   "coarse-current tally on the last inner" +
+                                   (f"; {world} axial planes, one per GPU" if world > 1 else ""),
+                       "mode": args.mode, "boundary_update": args.boundary, "segments": S, "resident_segments": n_useg,
+                       "n_reg": n_reg, "groups": G, "n_inner": n_inner, "updates_per_step": updates_step,
+                       "l2": "256 MB flush write between timed steps; device-resident inputs 450 MB > 126 MB L2",
+                       "kernel": "track" if args.kernel == 0 else "item"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(ln.item()),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_track_kernel",
+                         "launch": f"the track-kernel launches of one inner sweep of {groups_per_call} group(s)",
+                         "ms_per_launch": sweep_ms, "updates_per_launch": upd_per_sweep,
+                         "algorithmic_bytes_per_launch": bytes_contract,
+                         "resident_layout_bytes_per_launch": bytes_resident,
+                         "achieved_resident_layout": bytes_resident / (sweep_ms * 1e-3) / 1e9},
+            "cpu_baseline": cpu,
+        }))
+    sw.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,10 @@ extern "C" {
 #define MOCB200_EXP_FACTORED 1 /* same grid + linear interpolation, grid values from two bank-replicated
                                   factor tables (<= 2 ulp from the table entries) */
 
+/* sweep kernel selection (diagnostics / A-B measurements) */
+#define MOCB200_KERNEL_TRACK 0 /* one warp per track, both directions, affine scan over lanes */
+#define MOCB200_KERNEL_ITEM 1  /* one thread per (track, direction, group), serial walk */
+
 /*
  * Flattened ray-tracing data ("MOCFLAT"), produced once on the host from the
  * reference's RayData / CoreMesh / AngularQuadrature objects
@@ -141,7 +145,8 @@ typedef struct mocb200_options {
     int32_t block_threads;   /* 0 = default */
     int32_t plane_begin;     /* this rank's macroplane range [plane_begin, plane_end); both 0 = all */
     int32_t plane_end;
-    int32_t reserved[9];
+    int32_t kernel;          /* MOCB200_KERNEL_*; 0 = default (track kernel) */
+    int32_t reserved[8];
 } mocb200_options;
 
 /* Build the device-resident problem. The host arrays may be freed afterwards. */
@@ -205,6 +210,13 @@ int mocb200_get_stats(const mocb200_sweeper *h, mocb200_stats *out);
 /* Time (ms, CUDA events on the handle's stream) spent in transport-sweep kernels by the last
  * mocb200_sweep call; synchronises. */
 int mocb200_last_sweep_ms(mocb200_sweeper *h, double *ms);
+
+/* Cumulative device time of the transport-sweep kernels. While enabled, every inner iteration
+ * of mocb200_sweep is bracketed by a CUDA event pair on the handle's stream;
+ * mocb200_get_timing synchronises, returns the summed time (ms) and the number of inner sweeps
+ * since the last call, and resets both. */
+int mocb200_set_timing(mocb200_sweeper *h, int enabled);
+int mocb200_get_timing(mocb200_sweeper *h, double *sweep_ms, int64_t *inner_sweeps);
 
 /* Library/version string */
 const char *mocb200_version(void);

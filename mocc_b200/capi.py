@@ -18,6 +18,7 @@ MAX_POLAR = 4
 TALLY_NONE, TALLY_CURRENT, TALLY_CORRECTIONS = 0, 1, 2
 BOUNDARY_GS, BOUNDARY_JACOBI = 0, 1
 EXP_TABLE, EXP_FACTORED = 0, 1
+KERNEL_TRACK, KERNEL_ITEM = 0, 1
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -55,7 +56,7 @@ class Problem(C.Structure):
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("boundary_update", C.c_int32), ("exp_mode", C.c_int32),
                 ("max_polar", C.c_int32), ("block_threads", C.c_int32), ("plane_begin", C.c_int32),
-                ("plane_end", C.c_int32), ("reserved", C.c_int32 * 9)]
+                ("plane_end", C.c_int32), ("kernel", C.c_int32), ("reserved", C.c_int32 * 8)]
 
 
 class Stats(C.Structure):
@@ -120,6 +121,8 @@ def load_library(path=None):
     lib.mocb200_get_coarse.argtypes = [H, C.c_int, _f64p, _f64p]
     lib.mocb200_get_stats.argtypes = [H, C.POINTER(Stats)]
     lib.mocb200_last_sweep_ms.argtypes = [H, _f64p]
+    lib.mocb200_set_timing.argtypes = [H, C.c_int]
+    lib.mocb200_get_timing.argtypes = [H, _f64p, C.POINTER(C.c_int64)]
     lib.mocb200_version.restype = C.c_char_p
     if path == LIB_PATH:
         _lib = lib
@@ -141,7 +144,7 @@ class Sweeper:
     """Handle on a device-resident MoC problem (one GPU)."""
 
     def __init__(self, arrays, device=0, boundary_update=BOUNDARY_GS, exp_mode=EXP_TABLE, max_polar=0,
-                 block_threads=0, plane_begin=0, plane_end=0, lib=None):
+                 block_threads=0, plane_begin=0, plane_end=0, kernel=0, lib=None):
         self.lib = lib or load_library()
         self.arrays = arrays
         self.problem, self._keep = problem_from_arrays(arrays)
@@ -154,6 +157,7 @@ class Sweeper:
         opt.device, opt.boundary_update, opt.exp_mode = device, boundary_update, exp_mode
         opt.max_polar, opt.block_threads = max_polar, block_threads
         opt.plane_begin, opt.plane_end = plane_begin, plane_end
+        opt.kernel = kernel
         self.h = C.c_void_p()
         rc = self.lib.mocb200_create(C.byref(self.problem), C.byref(opt), C.byref(self.h))
         if rc != 0:
@@ -235,6 +239,15 @@ class Sweeper:
         return {"kernel_launches": s.kernel_launches, "sweep_launches": s.sweep_launches,
                 "segments_per_sweep": s.segments_per_sweep, "unique_segments": s.unique_segments,
                 "device_bytes": s.device_bytes, "items": [s.items[0], s.items[1]]}
+
+    def set_timing(self, enabled=True):
+        self._ck(self.lib.mocb200_set_timing(self.h, int(enabled)), "set_timing")
+
+    def get_timing(self):
+        """(summed sweep-kernel ms, inner sweeps) since the last call."""
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(self.lib.mocb200_get_timing(self.h, C.byref(ms), C.byref(n)), "get_timing")
+        return ms.value, n.value
 
     def last_sweep_ms(self):
         ms = C.c_double()

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "moc_kernels.cuh"
+#include "moc_track_kernel.cuh"
 
 using namespace mocb200;
 
@@ -21,6 +22,15 @@ thread_local std::string g_create_error;
 struct DeviceBuf {
     void *p      = nullptr;
     size_t bytes = 0;
+};
+
+struct TrackList { // one launch of the track kernel: units of one (unique plane, boundary phase, polar count)
+    int unique = 0, phase = 0, np = 0;
+    TrackUnit *d_units = nullptr;
+    int32_t n_units    = 0;
+    int32_t *d_planes  = nullptr;
+    int32_t n_planes   = 0;
+    int64_t segs       = 0; // reference segments (polar copies counted) swept per group, all planes
 };
 
 struct WorkList { // one kernel launch: items of one (unique plane, boundary phase, polar count)
@@ -66,11 +76,26 @@ struct mocb200_sweeper {
     uint32_t *d_counters = nullptr;
     int n_counters       = 0;
     std::vector<WorkList> lists;
+    // track kernel (production path)
+    int kernel = 0; // 0 = track kernel, 1 = item kernel
+    std::vector<TrackList> tlists;
+    double *d_pseg_len = nullptr; // segment arrays with every track padded to a multiple of 4
+    int32_t *d_pseg_fsr = nullptr;
+    int2 *d_xptr = nullptr;
+    Cross *d_xcross = nullptr;
+    double2 *d_xq = nullptr;
+    double *d_scratch = nullptr;
+    int scratch_per_warp = 0;
+    int max_nseg = 0;
+    int track_grid = 0;
     std::vector<bool> have_xs;
     // streams / events
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
+    bool timing   = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
     // stats
     mocb200_stats stats{};
     std::string error;
@@ -317,6 +342,117 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     h->stats.segments_per_sweep = segs_ref / 2;
     h->stats.unique_segments    = p.n_seg;
 
+    // ---- track kernel: padded geometry, crossing lists with sentinels, per-4-segment crossing pointers ----
+    h->kernel = opt.kernel;
+    if (h->kernel != MOCB200_KERNEL_TRACK && h->kernel != MOCB200_KERNEL_ITEM)
+        return fail(h, MOCB200_ERR_INVALID, "unknown kernel selection %d", h->kernel);
+    {
+        std::vector<int64_t> pbegin(p.n_trk + 1, 0);
+        for (int64_t t = 0; t < p.n_trk; t++) {
+            int64_t n = p.trk_seg_begin[t + 1] - p.trk_seg_begin[t];
+            if (n < 1)
+                return fail(h, MOCB200_ERR_INVALID, "track %lld has no segments", (long long)t);
+            h->max_nseg   = std::max<int>(h->max_nseg, (int)n);
+            pbegin[t + 1] = pbegin[t] + ((n + 3) & ~(int64_t)3);
+        }
+        const int64_t n_pseg = pbegin[p.n_trk];
+        if (n_pseg >= (int64_t)INT32_MAX)
+            return fail(h, MOCB200_ERR_INVALID, "padded segment count exceeds 32-bit indexing");
+        std::vector<double> plen((size_t)n_pseg, 0.0);
+        std::vector<int32_t> pfsr((size_t)n_pseg, 0);
+        std::vector<int2> xptr((size_t)(n_pseg / 4));
+        std::vector<Cross> xcross;
+        xcross.reserve(cross.size() + 2 * (size_t)p.n_trk);
+        const Cross sentinel{INT32_MAX, 0};
+        for (int64_t t = 0; t < p.n_trk; t++) {
+            const int64_t s0 = p.trk_seg_begin[t];
+            const int nseg   = (int)(p.trk_seg_begin[t + 1] - s0);
+            std::copy(p.seg_len + s0, p.seg_len + s0 + nseg, plen.begin() + pbegin[t]);
+            std::copy(p.seg_fsr + s0, p.seg_fsr + s0 + nseg, pfsr.begin() + pbegin[t]);
+            const int32_t f0 = (int32_t)xcross.size();
+            xcross.insert(xcross.end(), cross.begin() + cross_begin_fw[t], cross.begin() + cross_begin_fw[t] + cross_n_fw[t]);
+            xcross.push_back(sentinel);
+            const int32_t b0 = (int32_t)xcross.size();
+            xcross.insert(xcross.end(), cross.begin() + cross_begin_bw[t], cross.begin() + cross_begin_bw[t] + cross_n_bw[t]);
+            xcross.push_back(sentinel);
+            // first crossing at or after the first node a 4-segment group owns, in either walk order
+            int cf = f0, cb_hi = b0 + cross_n_bw[t]; // bwd pointers are found from the far end
+            std::vector<int32_t> bw_first((size_t)(nseg + 3) / 4);
+            for (int k0 = ((nseg - 1) / 4) * 4; k0 >= 0; k0 -= 4) {
+                const int nb_min = std::max(nseg - k0 - 4, 0);
+                // advance from the low end (nb ascending as k0 descends is NOT monotone here, so search)
+                int lo = b0, hi = cb_hi;
+                while (lo < hi) {
+                    int mid = (lo + hi) / 2;
+                    if (xcross[mid].node < nb_min)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                bw_first[k0 / 4] = lo;
+            }
+            for (int k0 = 0; k0 < nseg; k0 += 4) {
+                while (xcross[cf].node < k0)
+                    cf++;
+                xptr[(size_t)(pbegin[t] + k0) / 4] = make_int2(cf, bw_first[k0 / 4]);
+            }
+        }
+        int rc2;
+        if ((rc2 = dev_upload(h, &h->d_pseg_len, plen)) || (rc2 = dev_upload(h, &h->d_pseg_fsr, pfsr)) ||
+            (rc2 = dev_upload(h, &h->d_xptr, xptr)) || (rc2 = dev_upload(h, &h->d_xcross, xcross)))
+            return rc2;
+
+        for (int u = 0; u < p.n_unique; u++) {
+            std::vector<int32_t> planes;
+            for (int ip = h->plane_begin; ip < h->plane_end; ip++)
+                if (p.plane_unique[ip] == u)
+                    planes.push_back(ip);
+            if (planes.empty())
+                continue;
+            for (int phase = 0; phase < (jacobi ? 1 : 2); phase++) {
+                for (int np = 1; np <= kMaxPolar; np++) {
+                    std::vector<TrackUnit> units;
+                    for (size_t b = 0; b < bundles.size(); b++) {
+                        if (bundles[b].np != np || (!jacobi && bundle_phase[b] != phase))
+                            continue;
+                        int64_t t0 = p.geom_trk_begin[(size_t)u * p.n_geom + bundle_geom[b]];
+                        int64_t t1 = p.geom_trk_begin[(size_t)u * p.n_geom + bundle_geom[b] + 1];
+                        for (int64_t t = t0; t < t1; t++) {
+                            TrackUnit tu{};
+                            tu.seg_begin = (int32_t)pbegin[t];
+                            tu.nseg      = (int32_t)(p.trk_seg_begin[t + 1] - p.trk_seg_begin[t]);
+                            tu.bc0 = p.trk_bc[2 * t], tu.bc1 = p.trk_bc[2 * t + 1];
+                            tu.bundle = (int32_t)b;
+                            units.push_back(tu);
+                        }
+                    }
+                    if (units.empty())
+                        continue;
+                    std::stable_sort(units.begin(), units.end(),
+                                     [](const TrackUnit &x, const TrackUnit &y) { return x.nseg > y.nseg; });
+                    TrackList tl;
+                    tl.unique = u, tl.phase = phase, tl.np = np;
+                    tl.n_units  = (int32_t)units.size();
+                    tl.n_planes = (int32_t)planes.size();
+                    int64_t segs = 0;
+                    for (const auto &tu : units)
+                        segs += tu.nseg;
+                    tl.segs = segs * np * tl.n_planes;
+                    if ((int64_t)tl.n_units * tl.n_planes * p.n_group >= (int64_t)UINT32_MAX - 64)
+                        return fail(h, MOCB200_ERR_INVALID, "track list too large for 32-bit scheduling");
+                    if ((rc2 = dev_upload(h, &tl.d_units, units)) || (rc2 = dev_upload(h, &tl.d_planes, planes)))
+                        return rc2;
+                    h->tlists.push_back(tl);
+                }
+            }
+        }
+        h->track_grid       = h->sm_count;
+        h->scratch_per_warp = (h->max_nseg / 16 + 1) * 8 * kMaxPolar;
+        const size_t n_sc   = (size_t)h->track_grid * (kTrackBlock / 32) * h->scratch_per_warp;
+        if ((rc2 = dev_alloc(h, &h->d_scratch, n_sc)))
+            return rc2;
+    }
+
     // ---- uploads ----
     int rc;
 #define UP(dst, src, n)                                                                                      \
@@ -348,10 +484,16 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     UP(h->d_plane_first_reg, p.plane_first_reg, p.n_plane);
     UP(h->d_plane_surf_offset, p.plane_surf_offset, p.n_plane);
     UP(h->d_vol, p.vol, p.n_reg);
-    UP(h->d_exp, p.exp_table, p.exp_n + 2);
+    if ((rc = dev_alloc(h, &h->d_exp, (size_t)p.exp_n + 4))) // padded: the table is staged in 16-byte units
+        return rc;
+    CUDA_TRY(h, cudaMemset(h->d_exp, 0, ((size_t)p.exp_n + 4) * sizeof(double)));
+    CUDA_TRY(h, cudaMemcpy(h->d_exp, p.exp_table, ((size_t)p.exp_n + 2) * sizeof(double), cudaMemcpyHostToDevice));
 #undef UP
 
     const size_t nrg = (size_t)p.n_reg * h->GP;
+    if ((rc = dev_alloc(h, &h->d_xq, nrg)))
+        return rc;
+    CUDA_TRY(h, cudaMemset(h->d_xq, 0, nrg * sizeof(double2)));
     double **fsr_arrays[] = {&h->d_xstr, &h->d_xstr_src, &h->d_xs_self, &h->d_src, &h->d_flux, &h->d_qbar, &h->d_tally};
     for (double **arr : fsr_arrays) {
         if ((rc = dev_alloc(h, arr, nrg)))
@@ -376,7 +518,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     if ((rc = dev_alloc(h, &h->d_stage, h->stage_elems)))
         return rc;
     CUDA_TRY(h, cudaMallocHost((void **)&h->h_stage, h->stage_elems * sizeof(double)));
-    h->n_counters = (int)h->lists.size();
+    h->n_counters = (int)(h->lists.size() + h->tlists.size());
     if ((rc = dev_alloc(h, &h->d_counters, (size_t)h->n_counters)))
         return rc;
     h->have_xs.assign(p.n_group, false);
@@ -399,6 +541,33 @@ SweepFn pick_kernel(int np, int tally)
     case 9: return sweep_kernel<4, 1>;
     }
     return nullptr;
+}
+
+typedef void (*TrackFn)(const TrackArgs);
+
+template <int GL> TrackFn pick_track_gl(int np, int tally)
+{
+    switch (np * 2 + (tally ? 1 : 0)) {
+    case 2: return sweep_track_kernel<GL, 1, 4, 0>;
+    case 3: return sweep_track_kernel<GL, 1, 4, 1>;
+    case 4: return sweep_track_kernel<GL, 2, 4, 0>;
+    case 5: return sweep_track_kernel<GL, 2, 4, 1>;
+    case 6: return sweep_track_kernel<GL, 3, 4, 0>;
+    case 7: return sweep_track_kernel<GL, 3, 4, 1>;
+    case 8: return sweep_track_kernel<GL, 4, 4, 0>;
+    case 9: return sweep_track_kernel<GL, 4, 4, 1>;
+    }
+    return nullptr;
+}
+
+TrackFn pick_track_kernel(int gl, int np, int tally)
+{
+    return gl == 1 ? pick_track_gl<1>(np, tally) : pick_track_gl<8>(np, tally);
+}
+
+int track_smem_bytes(const mocb200_sweeper *h)
+{
+    return (((h->exp_n + 2) * (int)sizeof(double)) + 15) & ~15;
 }
 
 int check_groups(mocb200_sweeper *h, int g_begin, int g_count)
@@ -504,6 +673,17 @@ int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb
                 return MOCB200_ERR_CUDA;
             }
         }
+    for (int gl = 1; gl <= 8; gl *= 8)
+        for (int np = 1; np <= kMaxPolar; np++)
+            for (int t = 0; t < 2; t++) {
+                e = cudaFuncSetAttribute((const void *)pick_track_kernel(gl, np, t),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, track_smem_bytes(h));
+                if (e != cudaSuccess) {
+                    fail(nullptr, MOCB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+                    mocb200_destroy(h);
+                    return MOCB200_ERR_CUDA;
+                }
+            }
     *out = h;
     return MOCB200_OK;
 }
@@ -519,6 +699,10 @@ int mocb200_destroy(mocb200_sweeper *h)
         cudaFree(p);
     if (h->h_stage)
         cudaFreeHost(h->h_stage);
+    for (auto &pr : h->ev_pool) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
     if (h->ev0)
         cudaEventDestroy(h->ev0);
     if (h->ev1)
@@ -645,9 +829,14 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         const bool last = inner == n_inner - 1;
         const int tally = last ? tally_mode : MOCB200_TALLY_NONE;
         // q-bar and tally reset (whole FSR range: cheap, keeps indexing simple)
-        self_scatter_kernel<<<grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
-            h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_qbar, h->d_tally,
-            use_qbar ? 0 : 1);
+        if (h->kernel == MOCB200_KERNEL_TRACK)
+            self_scatter_xq_kernel<<<grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
+                h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_xstr,
+                h->d_qbar, h->d_xq, h->d_qbar, h->d_tally, use_qbar ? 0 : 1);
+        else
+            self_scatter_kernel<<<grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
+                h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_qbar,
+                h->d_tally, use_qbar ? 0 : 1);
         h->stats.kernel_launches++;
         if (tally == MOCB200_TALLY_CURRENT) {
             zero_groups_kernel<<<grid_for((int64_t)h->n_surf * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
@@ -659,9 +848,47 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * h->n_counters, h->stream));
         if (last)
             CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        if (h->timing) {
+            if (h->ev_used == h->ev_pool.size()) {
+                cudaEvent_t a = nullptr, b = nullptr;
+                CUDA_TRY(h, cudaEventCreate(&a));
+                CUDA_TRY(h, cudaEventCreate(&b));
+                h->ev_pool.emplace_back(a, b);
+            }
+            CUDA_TRY(h, cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream));
+        }
         const double *bc_in = h->d_bc[h->bc_cur];
         double *bc_out      = jacobi ? h->d_bc[1 - h->bc_cur] : h->d_bc[h->bc_cur];
-        for (int phase = 0; phase < (jacobi ? 1 : 2); phase++) {
+        for (int phase = 0; h->kernel == MOCB200_KERNEL_TRACK && phase < (jacobi ? 1 : 2); phase++) {
+            for (size_t il = 0; il < h->tlists.size(); il++) {
+                const TrackList &tl = h->tlists[il];
+                if (tl.phase != phase)
+                    continue;
+                const int gl = g_count <= 2 ? 1 : 8;
+                TrackArgs a{};
+                a.units = tl.d_units, a.n_units = tl.n_units, a.counter = h->d_counters + h->lists.size() + il;
+                a.bundles = h->d_bundles, a.planes = tl.d_planes, a.n_planes = tl.n_planes;
+                a.seg_len = h->d_pseg_len, a.seg_fsr = h->d_pseg_fsr, a.xptr = h->d_xptr, a.cross = h->d_xcross;
+                a.ang_rsintheta = h->d_rsin, a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
+                a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
+                a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
+                a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
+                a.n_ang = h->n_ang, a.bc_per_group = h->bcpg;
+                a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP, a.n_gsets = (g_count + gl - 1) / gl;
+                a.xq = h->d_xq, a.tally = h->d_tally;
+                a.bc_in = bc_in, a.bc_out = bc_out;
+                a.current = h->d_current, a.surface_flux = h->d_surfflux;
+                a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
+                a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
+                const int64_t warps = (int64_t)tl.n_units * tl.n_planes * a.n_gsets;
+                const int grid = (int)std::max<int64_t>(
+                    1, std::min<int64_t>((warps + kTrackBlock / 32 - 1) / (kTrackBlock / 32), h->track_grid));
+                pick_track_kernel(gl, tl.np, tally)<<<grid, kTrackBlock, track_smem_bytes(h), h->stream>>>(a);
+                h->stats.kernel_launches++;
+                h->stats.sweep_launches++;
+            }
+        }
+        for (int phase = 0; h->kernel == MOCB200_KERNEL_ITEM && phase < (jacobi ? 1 : 2); phase++) {
             for (size_t il = 0; il < h->lists.size(); il++) {
                 const WorkList &wl = h->lists[il];
                 if (wl.phase != phase)
@@ -688,6 +915,8 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 h->stats.sweep_launches++;
             }
         }
+        if (h->timing)
+            CUDA_TRY(h, cudaEventRecord(h->ev_pool[h->ev_used++].second, h->stream));
         if (last) {
             CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
             h->ev_valid = true;
@@ -735,6 +964,35 @@ int mocb200_last_sweep_ms(mocb200_sweeper *h, double *ms)
     float f = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&f, h->ev0, h->ev1));
     *ms = f;
+    return MOCB200_OK;
+}
+
+int mocb200_set_timing(mocb200_sweeper *h, int enabled)
+{
+    if (!h)
+        return MOCB200_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->timing  = enabled != 0;
+    h->ev_used = 0;
+    return MOCB200_OK;
+}
+
+int mocb200_get_timing(mocb200_sweeper *h, double *sweep_ms, int64_t *inner_sweeps)
+{
+    if (!h || !sweep_ms || !inner_sweeps)
+        return MOCB200_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i < h->ev_used; i++) {
+        float f = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&f, h->ev_pool[i].first, h->ev_pool[i].second));
+        tot += f;
+    }
+    *sweep_ms     = tot;
+    *inner_sweeps = (int64_t)h->ev_used;
+    h->ev_used    = 0;
     return MOCB200_OK;
 }
 

@@ -1,0 +1,76 @@
+// cuda_moc_sweeper.hpp -- the drop-in: a TransportSweeper that runs MOCC's 2-D MoC
+// transport sweep on a B200 through the C ABI of include/mocc_b200.h.
+//
+// Selected from the XML input with <sweeper type="moc_cuda" ...> (see
+// transport_sweeper_factory.cpp in this directory). It derives from the reference's
+// moc::MoCSweeper (src/sweepers/moc/moc_sweeper.hpp:36-234) and overrides exactly the hot
+// path, MoCSweeper::sweep (moc_sweeper.cpp:189-225): ray tracing, boundary-condition
+// objects, pin homogenisation/prolongation, transverse leakage, fission source and output
+// are inherited unchanged, so the rest of MOCC (EigenSolver, FixedSourceSolver, CMFD, 2D3D)
+// runs as is. Host-visible state (flux_, boundary_, CoarseData) is refreshed after every
+// sweep(group) because the callers read it between sweeps (transport_sweeper.hpp:139-150,
+// source.cpp:26-32).
+//
+// Options live on a <cuda> child of <sweeper> so that the reference's attribute validation
+// (moc_sweeper.cpp:54-57, util/validate_input.cpp:24-42) stays quiet:
+//   <cuda device="0" group_batch="f" kernel="track" max_polar="2"/>
+//     group_batch="t": sweep(0..ng-2) only stage their sources; sweep(ng-1) sweeps all groups
+//                      in one batch (Jacobi instead of Gauss-Seidel in energy: same converged
+//                      answer, different iteration path).
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "pugixml.hpp"
+
+#include "core/core_mesh.hpp"
+#include "sweepers/moc/moc_sweeper.hpp"
+
+#include "mocc_b200.h"
+
+namespace mocc_b200 {
+
+class CudaMoCSweeper : public mocc::moc::MoCSweeper {
+public:
+    CudaMoCSweeper(const pugi::xml_node &input, const mocc::CoreMesh &mesh);
+    ~CudaMoCSweeper();
+
+    void sweep(int group) override;
+
+    // Device time spent in transport-sweep kernels / number of C-ABI sweeps so far
+    double device_sweep_ms() const
+    {
+        return device_sweep_ms_;
+    }
+    const mocb200_stats &device_stats();
+
+protected:
+    // What the last inner iteration of a sweep tallies; the 2D3D variant overrides this
+    virtual int tally_mode() const
+    {
+        return coarse_data_ ? MOCB200_TALLY_CURRENT : MOCB200_TALLY_NONE;
+    }
+    // Hook called after the device results of `group` are back on the host
+    virtual void post_group(int group)
+    {
+        (void)group;
+    }
+
+    void check(int rc, const char *what) const;
+    void upload_group(int group);
+    void download_group(int group, int tally);
+
+    mocb200_sweeper *dev_ = nullptr;
+    bool group_batch_     = false;
+    int n_bc_             = 0; // boundary values per group per plane
+    int n_macroplane_     = 0;
+    // per-FSR cross sections, [n_group][n_reg]
+    std::vector<double> xstr_true_fsr_; // un-split transport XS (source normalisation)
+    std::vector<double> xs_self_fsr_;   // within-group scattering
+    std::vector<bool> xs_uploaded_;
+    std::vector<double> col_, cur_, sflux_;
+    double device_sweep_ms_ = 0.0;
+    mocb200_stats stats_{};
+};
+}

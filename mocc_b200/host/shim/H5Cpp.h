@@ -1,7 +1,7 @@
 // No-op stand-in for the HDF5 C++ API surface that MOCC's H5Node wrapper
 // (src/util/h5file.hpp:101-409, h5file.cpp:24-268) touches.
 //
-// TEST INFRASTRUCTURE ONLY: HDF5 is an external dependency of the reference
+// BUILD SHIM: HDF5 is an external dependency of the reference
 // (CMakeLists.txt:103) that is not installed in this image. Writes are
 // discarded, reads throw (so any code path that needs real HDF5 input fails
 // loudly instead of silently producing garbage). Results are compared

@@ -1,10 +1,10 @@
 // Minimal stand-in for the subset of Blitz++ that MOCC (youngmit/mocc) uses.
 //
-// TEST INFRASTRUCTURE ONLY. Blitz++ is an external dependency of the
+// BUILD SHIM. Blitz++ is an external dependency of the
 // reference (cmake/FindBlitz.cmake, src/util/blitz_typedefs.hpp:19) that is
 // not vendored under /root/reference and not installed in this image. This
-// header exists so that the UNMODIFIED reference sources can be compiled into
-// oracle/_ref/ (see oracle/Makefile). It is an original implementation written
+// header exists so that the UNMODIFIED reference sources can be compiled here (the
+// oracle build oracle/Makefile and the plugin build mocc_b200/host/Makefile). Original, written
 // against Blitz's documented semantics, not a copy of Blitz:
 //   * Array<T,N>: reference-counted storage, row-major, zero-based
 //   * copy construction is SHALLOW (a view); operator=(Array) is a DEEP

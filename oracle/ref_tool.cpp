@@ -5,7 +5,8 @@
 //   golden  <in.xml> <out_prefix>               flat file + per-sweep1g records produced by the
 //                                               reference kernel (moc_sweeper_kernel.inc.hpp:36-180)
 //   solve   <in.xml> <out.golden>               run the reference solver unchanged; dump k, flux
-//   time    <in.xml> [--sweeps N]               time the reference CPU sweep (JSON to stdout)
+//   time    <in.xml> [--sweeps N] [--warmup W]  time N passes (every group once, n_inner inners each) of the
+//                                               reference CPU sweep after W untimed passes (JSON to stdout)
 // Options (any command):
 //   --set path/to/node@attr=value               amend the XML before it is parsed
 //   --outers N  --records "o:g:i,o:g:i,..."     (golden) outer iterations; which sweeps to record
@@ -239,7 +240,7 @@ int main(int argc, char **argv)
         std::string cmd = argv[1], xml = argv[2];
         std::string out_path;
         std::vector<std::string> sets;
-        int outers = 1, sweeps = 2;
+        int outers = 1, sweeps = 2, warmup = 1;
         bool cmfd  = false;
         std::string records;
         for (int i = 3; i < argc; i++) {
@@ -250,6 +251,8 @@ int main(int argc, char **argv)
                 outers = std::atoi(argv[++i]);
             else if (a == "--sweeps" && i + 1 < argc)
                 sweeps = std::atoi(argv[++i]);
+            else if (a == "--warmup" && i + 1 < argc)
+                warmup = std::atoi(argv[++i]);
             else if (a == "--records" && i + 1 < argc)
                 records = argv[++i];
             else if (a == "--cmfd")
@@ -371,7 +374,8 @@ int main(int argc, char **argv)
                     sw.sweep(ig);
                 }
             };
-            pass();
+            for (int i = 0; i < warmup; i++)
+                pass();
             auto t0 = std::chrono::steady_clock::now();
             for (int i = 0; i < sweeps; i++)
                 pass();

@@ -63,10 +63,11 @@ def _xy_mask(flat):
 
 @pytest.mark.parametrize("case", sorted(CASES))
 @pytest.mark.parametrize("max_polar", [1, 2, 4])
-def test_sweep1g_matches_reference_golden(case, max_polar):
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_sweep1g_matches_reference_golden(case, max_polar, kernel):
     flat, gold = load_case(case)
     gs = bool(gold["gs_boundary"][0])
-    sw = _sweeper(flat, boundary_update=0 if gs else 1, max_polar=max_polar)
+    sw = _sweeper(flat, boundary_update=0 if gs else 1, max_polar=max_polar, kernel=kernel)
     xy = _xy_mask(flat)
     for rec in records(gold):
         flux, bc_out, cur, sf = _run_record(sw, flat, rec)
@@ -92,7 +93,8 @@ def test_self_scatter_then_sweep_matches_reference(case):
 
 @pytest.mark.parametrize("case", ["mini2d_gs", "mini3d_gs"])
 @pytest.mark.parametrize("jacobi", [False, True])
-def test_batched_groups_match_oracle(case, jacobi):
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_batched_groups_match_oracle(case, jacobi, kernel):
     """All groups in one launch (groups across lanes) == the oracle run group by group."""
     flat, gold = load_case(case)
     G, n_reg, n_plane = (int(flat[k][0]) for k in ("n_group", "n_reg", "n_plane"))
@@ -101,7 +103,7 @@ def test_batched_groups_match_oracle(case, jacobi):
     xstr = np.stack([gold[f"xs_tr_{g}"] for g in range(G)])
     qbar = rng.uniform(0.05, 1.0, size=(G, n_reg))
     bc = rng.uniform(0.0, 0.3, size=(n_plane, G, bcpg))
-    sw = _sweeper(flat, boundary_update=1 if jacobi else 0)
+    sw = _sweeper(flat, boundary_update=1 if jacobi else 0, kernel=kernel)
     sw.set_xs(0, xstr)
     sw.set_qbar(0, qbar)
     for ip in range(n_plane):
