@@ -57,8 +57,10 @@ extern "C" {
                                   factor tables (<= 2 ulp from the table entries) */
 
 /* sweep kernel selection (diagnostics / A-B measurements) */
-#define MOCB200_KERNEL_TRACK 0 /* one warp per track, both directions, affine scan over lanes */
-#define MOCB200_KERNEL_ITEM 1  /* one thread per (track, direction, group), serial walk */
+#define MOCB200_KERNEL_AUTO 0   /* CACHED when the attenuation cache fits in device memory, else TRACK */
+#define MOCB200_KERNEL_ITEM 1   /* one thread per (track, direction, group), serial walk */
+#define MOCB200_KERNEL_TRACK 2  /* one warp per track, both directions, affine scan over lanes */
+#define MOCB200_KERNEL_CACHED 3 /* TRACK with the table lookups cached in HBM per cross-section upload */
 
 /*
  * Flattened ray-tracing data ("MOCFLAT"), produced once on the host from the
@@ -145,7 +147,7 @@ typedef struct mocb200_options {
     int32_t block_threads;   /* 0 = default */
     int32_t plane_begin;     /* this rank's macroplane range [plane_begin, plane_end); both 0 = all */
     int32_t plane_end;
-    int32_t kernel;          /* MOCB200_KERNEL_*; 0 = default (track kernel) */
+    int32_t kernel;          /* MOCB200_KERNEL_* */
     int32_t reserved[8];
 } mocb200_options;
 

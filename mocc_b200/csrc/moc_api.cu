@@ -12,6 +12,7 @@
 
 #include "moc_kernels.cuh"
 #include "moc_track_kernel.cuh"
+#include "moc_cached_kernel.cuh"
 
 using namespace mocb200;
 
@@ -31,6 +32,8 @@ struct TrackList { // one launch of the track kernel: units of one (unique plane
     int32_t *d_planes  = nullptr;
     int32_t n_planes   = 0;
     int64_t segs       = 0; // reference segments (polar copies counted) swept per group, all planes
+    int64_t pseg       = 0; // padded segments of all units (cache positions)
+    double *d_cache    = nullptr; // attenuation cache of this list (CACHED kernel)
 };
 
 struct WorkList { // one kernel launch: items of one (unique plane, boundary phase, polar count)
@@ -77,7 +80,10 @@ struct mocb200_sweeper {
     int n_counters       = 0;
     std::vector<WorkList> lists;
     // track kernel (production path)
-    int kernel = 0; // 0 = track kernel, 1 = item kernel
+    int kernel = 0;       // MOCB200_KERNEL_* actually used
+    int cache_layout = 0; // 0 = no cache allocated, 1 = group-major (GL 1), 8 = group-fastest (GL 8)
+    std::vector<bool> cache_valid; // per group
+    double *d_qg = nullptr, *d_tg = nullptr; // group-major q-bar / tally [G][n_reg]
     std::vector<TrackList> tlists;
     double *d_pseg_len = nullptr; // segment arrays with every track padded to a multiple of 4
     int32_t *d_pseg_fsr = nullptr;
@@ -344,7 +350,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
 
     // ---- track kernel: padded geometry, crossing lists with sentinels, per-4-segment crossing pointers ----
     h->kernel = opt.kernel;
-    if (h->kernel != MOCB200_KERNEL_TRACK && h->kernel != MOCB200_KERNEL_ITEM)
+    if (h->kernel < MOCB200_KERNEL_AUTO || h->kernel > MOCB200_KERNEL_CACHED)
         return fail(h, MOCB200_ERR_INVALID, "unknown kernel selection %d", h->kernel);
     {
         std::vector<int64_t> pbegin(p.n_trk + 1, 0);
@@ -431,6 +437,10 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                     std::stable_sort(units.begin(), units.end(),
                                      [](const TrackUnit &x, const TrackUnit &y) { return x.nseg > y.nseg; });
                     TrackList tl;
+                    for (auto &tu : units) {
+                        tu.pad0 = (int32_t)tl.pseg;
+                        tl.pseg += (tu.nseg + 3) & ~3;
+                    }
                     tl.unique = u, tl.phase = phase, tl.np = np;
                     tl.n_units  = (int32_t)units.size();
                     tl.n_planes = (int32_t)planes.size();
@@ -522,6 +532,22 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     if ((rc = dev_alloc(h, &h->d_counters, (size_t)h->n_counters)))
         return rc;
     h->have_xs.assign(p.n_group, false);
+    h->cache_valid.assign(p.n_group, false);
+    if ((rc = dev_alloc(h, &h->d_qg, (size_t)p.n_group * p.n_reg)) || (rc = dev_alloc(h, &h->d_tg, (size_t)p.n_group * p.n_reg)))
+        return rc;
+    if (h->kernel == MOCB200_KERNEL_AUTO || h->kernel == MOCB200_KERNEL_CACHED) {
+        // the attenuation cache: 8 bytes per (padded segment, polar angle, group, plane)
+        int64_t bytes = 0;
+        for (const auto &tl : h->tlists)
+            bytes += tl.pseg * tl.np * tl.n_planes * (int64_t)h->GP * 8;
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
+        const bool fits = (double)bytes < 0.8 * (double)free_b;
+        if (!fits && h->kernel == MOCB200_KERNEL_CACHED)
+            return fail(h, MOCB200_ERR_INVALID, "attenuation cache (%lld MiB) does not fit in device memory",
+                        (long long)(bytes >> 20));
+        h->kernel = fits ? MOCB200_KERNEL_CACHED : MOCB200_KERNEL_TRACK;
+    }
     h->stats.device_bytes = h->device_bytes;
     return MOCB200_OK;
 }
@@ -563,6 +589,28 @@ template <int GL> TrackFn pick_track_gl(int np, int tally)
 TrackFn pick_track_kernel(int gl, int np, int tally)
 {
     return gl == 1 ? pick_track_gl<1>(np, tally) : pick_track_gl<8>(np, tally);
+}
+
+typedef void (*CachedFn)(const CachedArgs);
+
+template <int GL> CachedFn pick_cached_gl(int np, int tally)
+{
+    switch (np * 2 + (tally ? 1 : 0)) {
+    case 2: return sweep_cached_kernel<GL, 1, 0>;
+    case 3: return sweep_cached_kernel<GL, 1, 1>;
+    case 4: return sweep_cached_kernel<GL, 2, 0>;
+    case 5: return sweep_cached_kernel<GL, 2, 1>;
+    case 6: return sweep_cached_kernel<GL, 3, 0>;
+    case 7: return sweep_cached_kernel<GL, 3, 1>;
+    case 8: return sweep_cached_kernel<GL, 4, 0>;
+    case 9: return sweep_cached_kernel<GL, 4, 1>;
+    }
+    return nullptr;
+}
+
+CachedFn pick_cached_kernel(int gl, int np, int tally)
+{
+    return gl == 1 ? pick_cached_gl<1>(np, tally) : pick_cached_gl<8>(np, tally);
 }
 
 int track_smem_bytes(const mocb200_sweeper *h)
@@ -673,6 +721,12 @@ int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb
                 return MOCB200_ERR_CUDA;
             }
         }
+    e = cudaFuncSetAttribute((const void *)exp_cache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+        fail(nullptr, MOCB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        mocb200_destroy(h);
+        return MOCB200_ERR_CUDA;
+    }
     for (int gl = 1; gl <= 8; gl *= 8)
         for (int np = 1; np <= kMaxPolar; np++)
             for (int t = 0; t < 2; t++) {
@@ -697,6 +751,9 @@ int mocb200_destroy(mocb200_sweeper *h)
         cudaStreamSynchronize(h->own_stream);
     for (void *p : h->allocs)
         cudaFree(p);
+    for (auto &tl : h->tlists)
+        if (tl.d_cache)
+            cudaFree(tl.d_cache);
     if (h->h_stage)
         cudaFreeHost(h->h_stage);
     for (auto &pr : h->ev_pool) {
@@ -747,8 +804,10 @@ int mocb200_set_xs(mocb200_sweeper *h, int g_begin, int g_count, const double *x
         return rc;
     if ((rc = upload_columns(h, xs_self, h->n_reg, g_begin, g_count, h->d_xs_self)))
         return rc;
-    for (int g = g_begin; g < g_begin + g_count; g++)
-        h->have_xs[g] = true;
+    for (int g = g_begin; g < g_begin + g_count; g++) {
+        h->have_xs[g]     = true;
+        h->cache_valid[g] = false;
+    }
     return MOCB200_OK;
 }
 
@@ -825,16 +884,69 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
     const int smem    = (h->exp_n + 2) * (int)sizeof(double);
     const int64_t nrg = (int64_t)(h->reg_hi - h->reg_lo) * g_count;
 
+    const int gl          = g_count <= 2 ? 1 : 8; // group lanes per segment (track / cached kernels)
+    const int n_gsets     = (g_count + gl - 1) / gl;
+    const bool cached     = h->kernel == MOCB200_KERNEL_CACHED;
+    const bool group_major = cached && gl == 1;
+
+    if (cached) {
+        // (re)build the attenuation cache for groups whose cross sections changed
+        if (h->cache_layout != gl) {
+            for (auto &tl : h->tlists) {
+                if (tl.d_cache) {
+                    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+                    CUDA_TRY(h, cudaFree(tl.d_cache));
+                    h->device_bytes -= tl.pseg * tl.np * tl.n_planes * (int64_t)(h->cache_layout == 1 ? h->G : h->GP) * 8;
+                    tl.d_cache = nullptr;
+                }
+                const size_t bytes = (size_t)tl.pseg * tl.np * tl.n_planes * (gl == 1 ? h->G : h->GP) * 8;
+                CUDA_TRY(h, cudaMalloc((void **)&tl.d_cache, bytes));
+                h->device_bytes += (int64_t)bytes;
+            }
+            h->cache_layout = gl;
+            h->cache_valid.assign(h->G, false);
+            h->stats.device_bytes = h->device_bytes;
+        }
+        bool dirty = false;
+        for (int g = g_begin; g < g_begin + g_count; g++)
+            dirty = dirty || !h->cache_valid[g];
+        if (dirty) {
+            for (const auto &tl : h->tlists) {
+                CacheArgs c{};
+                c.units = tl.d_units, c.n_units = tl.n_units, c.bundles = h->d_bundles;
+                c.planes = tl.d_planes, c.n_planes = tl.n_planes;
+                c.seg_len = h->d_pseg_len, c.seg_fsr = h->d_pseg_fsr, c.ang_rsintheta = h->d_rsin;
+                c.plane_first_reg = h->d_plane_first_reg, c.xstr = h->d_xstr;
+                c.g_begin = g_begin, c.g_count = g_count, c.g_cache_begin = 0, c.g_cache_count = h->G;
+                c.GP = h->GP, c.np = tl.np, c.group_major = gl == 1 ? 1 : 0;
+                c.cache = tl.d_cache, c.list_pseg = tl.pseg;
+                c.exp_table = h->d_exp, c.exp_n = h->exp_n, c.exp_min = h->exp_min, c.exp_max = h->exp_max;
+                const int64_t warps = (int64_t)tl.n_units * tl.n_planes;
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 15) / 16, h->sm_count));
+                exp_cache_kernel<<<grid, 512, smem, h->stream>>>(c);
+                h->stats.kernel_launches++;
+            }
+            for (int g = g_begin; g < g_begin + g_count; g++)
+                h->cache_valid[g] = true;
+        }
+    }
+
     for (int inner = 0; inner < n_inner; inner++) {
         const bool last = inner == n_inner - 1;
         const int tally = last ? tally_mode : MOCB200_TALLY_NONE;
         // q-bar and tally reset (whole FSR range: cheap, keeps indexing simple)
-        if (h->kernel == MOCB200_KERNEL_TRACK)
-            self_scatter_xq_kernel<<<grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
+        const int ss_grid = grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count);
+        if (cached)
+            self_scatter_q_kernel<<<ss_grid, 256, 0, h->stream>>>(
+                h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_qbar,
+                group_major ? h->d_qg : h->d_qbar, group_major ? h->d_tg : h->d_tally, group_major ? 1 : 0,
+                use_qbar ? 0 : 1);
+        else if (h->kernel == MOCB200_KERNEL_TRACK)
+            self_scatter_xq_kernel<<<ss_grid, 256, 0, h->stream>>>(
                 h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_xstr,
                 h->d_qbar, h->d_xq, h->d_qbar, h->d_tally, use_qbar ? 0 : 1);
         else
-            self_scatter_kernel<<<grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
+            self_scatter_kernel<<<ss_grid, 256, 0, h->stream>>>(
                 h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_qbar,
                 h->d_tally, use_qbar ? 0 : 1);
         h->stats.kernel_launches++;
@@ -859,58 +971,77 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         }
         const double *bc_in = h->d_bc[h->bc_cur];
         double *bc_out      = jacobi ? h->d_bc[1 - h->bc_cur] : h->d_bc[h->bc_cur];
-        for (int phase = 0; h->kernel == MOCB200_KERNEL_TRACK && phase < (jacobi ? 1 : 2); phase++) {
+        for (int phase = 0; phase < (jacobi ? 1 : 2); phase++) {
+            if (h->kernel == MOCB200_KERNEL_ITEM) {
+                for (size_t il = 0; il < h->lists.size(); il++) {
+                    const WorkList &wl = h->lists[il];
+                    if (wl.phase != phase)
+                        continue;
+                    SweepArgs a{};
+                    a.items = wl.d_items, a.n_items = wl.n_items, a.counter = h->d_counters + il;
+                    a.bundles = h->d_bundles, a.planes = wl.d_planes, a.n_planes = wl.n_planes;
+                    a.seg_len = h->d_seg_len, a.seg_fsr = h->d_seg_fsr, a.cross = h->d_cross;
+                    a.ang_rsintheta = h->d_rsin, a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
+                    a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
+                    a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
+                    a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
+                    a.n_ang = h->n_ang, a.bc_per_group = h->bcpg;
+                    a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP;
+                    a.xstr = h->d_xstr, a.qbar = h->d_qbar, a.tally = h->d_tally;
+                    a.bc_in = bc_in, a.bc_out = bc_out;
+                    a.current = h->d_current, a.surface_flux = h->d_surfflux;
+                    a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
+                    const int64_t threads = (int64_t)wl.n_items * wl.n_planes * g_count;
+                    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((threads + block - 1) / block,
+                                                                                (int64_t)h->sm_count * 2));
+                    pick_kernel(wl.np, tally)<<<grid, block, smem, h->stream>>>(a);
+                    h->stats.kernel_launches++;
+                    h->stats.sweep_launches++;
+                }
+                continue;
+            }
             for (size_t il = 0; il < h->tlists.size(); il++) {
                 const TrackList &tl = h->tlists[il];
                 if (tl.phase != phase)
                     continue;
-                const int gl = g_count <= 2 ? 1 : 8;
-                TrackArgs a{};
-                a.units = tl.d_units, a.n_units = tl.n_units, a.counter = h->d_counters + h->lists.size() + il;
-                a.bundles = h->d_bundles, a.planes = tl.d_planes, a.n_planes = tl.n_planes;
-                a.seg_len = h->d_pseg_len, a.seg_fsr = h->d_pseg_fsr, a.xptr = h->d_xptr, a.cross = h->d_xcross;
-                a.ang_rsintheta = h->d_rsin, a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
-                a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
-                a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
-                a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
-                a.n_ang = h->n_ang, a.bc_per_group = h->bcpg;
-                a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP, a.n_gsets = (g_count + gl - 1) / gl;
-                a.xq = h->d_xq, a.tally = h->d_tally;
-                a.bc_in = bc_in, a.bc_out = bc_out;
-                a.current = h->d_current, a.surface_flux = h->d_surfflux;
-                a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
-                a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
-                const int64_t warps = (int64_t)tl.n_units * tl.n_planes * a.n_gsets;
-                const int grid = (int)std::max<int64_t>(
-                    1, std::min<int64_t>((warps + kTrackBlock / 32 - 1) / (kTrackBlock / 32), h->track_grid));
-                pick_track_kernel(gl, tl.np, tally)<<<grid, kTrackBlock, track_smem_bytes(h), h->stream>>>(a);
-                h->stats.kernel_launches++;
-                h->stats.sweep_launches++;
-            }
-        }
-        for (int phase = 0; h->kernel == MOCB200_KERNEL_ITEM && phase < (jacobi ? 1 : 2); phase++) {
-            for (size_t il = 0; il < h->lists.size(); il++) {
-                const WorkList &wl = h->lists[il];
-                if (wl.phase != phase)
-                    continue;
-                SweepArgs a{};
-                a.items = wl.d_items, a.n_items = wl.n_items, a.counter = h->d_counters + il;
-                a.bundles = h->d_bundles, a.planes = wl.d_planes, a.n_planes = wl.n_planes;
-                a.seg_len = h->d_seg_len, a.seg_fsr = h->d_seg_fsr, a.cross = h->d_cross;
-                a.ang_rsintheta = h->d_rsin, a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
-                a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
-                a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
-                a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
-                a.n_ang = h->n_ang, a.bc_per_group = h->bcpg;
-                a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP;
-                a.xstr = h->d_xstr, a.qbar = h->d_qbar, a.tally = h->d_tally;
-                a.bc_in = bc_in, a.bc_out = bc_out;
-                a.current = h->d_current, a.surface_flux = h->d_surfflux;
-                a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
-                const int64_t threads = (int64_t)wl.n_items * wl.n_planes * g_count;
-                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((threads + block - 1) / block,
-                                                                            (int64_t)h->sm_count * 2));
-                pick_kernel(wl.np, tally)<<<grid, block, smem, h->stream>>>(a);
+                const int64_t warps = (int64_t)tl.n_units * tl.n_planes * n_gsets;
+                const int grid      = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 15) / 16, h->track_grid));
+                uint32_t *counter   = h->d_counters + h->lists.size() + il;
+                if (cached) {
+                    CachedArgs a{};
+                    a.units = tl.d_units, a.n_units = tl.n_units, a.counter = counter;
+                    a.bundles = h->d_bundles, a.planes = tl.d_planes, a.n_planes = tl.n_planes;
+                    a.seg_fsr = h->d_pseg_fsr, a.xptr = h->d_xptr, a.cross = h->d_xcross;
+                    a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
+                    a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
+                    a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
+                    a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
+                    a.n_ang = h->n_ang, a.bc_per_group = h->bcpg;
+                    a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP, a.n_gsets = n_gsets, a.n_reg = h->n_reg;
+                    a.q = group_major ? h->d_qg : h->d_qbar, a.tally = group_major ? h->d_tg : h->d_tally;
+                    a.bc_in = bc_in, a.bc_out = bc_out;
+                    a.current = h->d_current, a.surface_flux = h->d_surfflux;
+                    a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
+                    a.cache = tl.d_cache, a.list_pseg = tl.pseg, a.cache_groups = h->G;
+                    pick_cached_kernel(gl, tl.np, tally)<<<grid, kCachedBlock, 0, h->stream>>>(a);
+                } else {
+                    TrackArgs a{};
+                    a.units = tl.d_units, a.n_units = tl.n_units, a.counter = counter;
+                    a.bundles = h->d_bundles, a.planes = tl.d_planes, a.n_planes = tl.n_planes;
+                    a.seg_len = h->d_pseg_len, a.seg_fsr = h->d_pseg_fsr, a.xptr = h->d_xptr, a.cross = h->d_xcross;
+                    a.ang_rsintheta = h->d_rsin, a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
+                    a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
+                    a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
+                    a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
+                    a.n_ang = h->n_ang, a.bc_per_group = h->bcpg;
+                    a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP, a.n_gsets = n_gsets;
+                    a.xq = h->d_xq, a.tally = h->d_tally;
+                    a.bc_in = bc_in, a.bc_out = bc_out;
+                    a.current = h->d_current, a.surface_flux = h->d_surfflux;
+                    a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
+                    a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
+                    pick_track_kernel(gl, tl.np, tally)<<<grid, kTrackBlock, track_smem_bytes(h), h->stream>>>(a);
+                }
                 h->stats.kernel_launches++;
                 h->stats.sweep_launches++;
             }
@@ -923,9 +1054,9 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         }
         if (jacobi)
             h->bc_cur = 1 - h->bc_cur;
-        finalize_flux_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
-            h->n_reg, h->GP, g_begin, g_count, h->d_tally, h->d_xstr, h->d_vol, h->d_qbar, h->d_flux, nullptr, h->reg_lo,
-            h->reg_hi);
+        finalize_flux_q_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
+            h->n_reg, h->GP, g_begin, g_count, group_major ? h->d_tg : h->d_tally, h->d_xstr, h->d_vol, h->d_qbar,
+            h->d_flux, h->reg_lo, h->reg_hi, group_major ? 1 : 0);
         h->stats.kernel_launches++;
         CUDA_TRY(h, cudaGetLastError());
     }
