@@ -19,7 +19,9 @@
  *                                + BoundaryCondition::update          core/source_isotropic.cpp:21-57,
  *                                                                     core/boundary_condition.cpp:145-191
  *   mocb200_get_coarse        <- moc::Current::post_ray tallies       sweepers/moc/moc_current_worker.hpp:202-264
- *   mocb200_get_corrections   <- cmdo::CurrentCorrections tallies     sweepers/cmdo/correction_worker.hpp:109-246
+ *   mocb200_set_sn_xs,
+ *   mocb200_get_corrections   <- cmdo::CurrentCorrections                sweepers/cmdo/correction_worker.hpp:109-246,
+ *                                                                     sweepers/cmdo/correction_worker.cpp:32-158
  *
  * All floating point data is FP64, all indices int32 unless stated (the
  * reference: real_t = double, util/global_config.hpp:27-33).
@@ -134,6 +136,14 @@ typedef struct mocb200_problem {
 
     /* ---- exponential table [exp_n + 2]: exp(exp_min + i*space), last entry repeated ---- */
     const double *exp_table;
+
+    /* ---- 2D3D correction factors (cmdo::CurrentCorrections, correction_worker.cpp:32-158).
+     *      Optional: all five NULL disables MOCB200_TALLY_CORRECTIONS. ---- */
+    const double *ang_area_x; /* [n_ang] abs(spacing/cos(alpha)), correction_worker.cpp:78-79 */
+    const double *ang_area_y; /* [n_ang] abs(spacing/sin(alpha)) */
+    const double *ang_ox;     /* [n_ang] Angle::ox (only its sign is used, :47-66) */
+    const double *cell_dx;    /* [n_cell_plane] Mesh::pin_dx()[coarse_position(cell).x] */
+    const double *cell_dy;    /* [n_cell_plane] Mesh::pin_dy()[coarse_position(cell).y] */
 } mocb200_problem;
 
 typedef struct mocb200_sweeper mocb200_sweeper; /* opaque */
@@ -197,6 +207,20 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
  * this handle's macroplanes only, NOT yet divided by the surface area -- the reference does
  * that in post_sweep, moc_current_worker.hpp:272-318). */
 int mocb200_get_coarse(mocb200_sweeper *h, int group, double *current, double *surface_flux);
+
+/*
+ * 2D3D coupling (MoCSweeper_2D3D, cmdo/moc_sweeper_2d3d.cpp:48-99).
+ *   mocb200_set_sn_xs        homogenised transport XS of the Sn mesh the beta factor divides by
+ *                            (xstr_sn_[cell + mplane_offset], correction_worker.cpp:84-93): host array
+ *                            [g_count][n_plane*n_cell_plane], macroplane-major.
+ *   mocb200_get_corrections  correction factors of the last MOCB200_TALLY_CORRECTIONS sweep of `group`:
+ *                            alpha[2*n_ang][n_plane*n_cell_plane][2] (X, Y normal), beta[2*n_ang][n_plane*n_cell_plane],
+ *                            angle index = sweep angle (forward) or sweep angle + n_ang (its reverse), cell index =
+ *                            cell + Mesh::coarse_cell_offset(macroplane). Entries of macroplanes outside this handle's
+ *                            range are left untouched.
+ */
+int mocb200_set_sn_xs(mocb200_sweeper *h, int g_begin, int g_count, const double *xs);
+int mocb200_get_corrections(mocb200_sweeper *h, int group, double *alpha, double *beta);
 
 /* Counters for bench/diagnostics */
 typedef struct mocb200_stats {

@@ -45,7 +45,9 @@ _ARRAYS = [
     ("plane_surf_offset", _i32p),
     ("coarse_surf", _i32p), ("coarse_nbr", _i32p),
     ("vol", _f64p), ("exp_table", _f64p),
+    ("ang_area_x", _f64p), ("ang_area_y", _f64p), ("ang_ox", _f64p), ("cell_dx", _f64p), ("cell_dy", _f64p),
 ]
+_OPTIONAL = {"ang_area_x", "ang_area_y", "ang_ox", "cell_dx", "cell_dy"}
 _NP = {_i32p: np.int32, _i64p: np.int64, _u32p: np.uint32, _f64p: np.float64}
 
 
@@ -83,6 +85,8 @@ def problem_from_arrays(arrays):
             v = scalar(arrays, name)
         setattr(p, name, v)
     for name, ct in _ARRAYS:
+        if name in _OPTIONAL and name not in arrays:
+            continue  # stays NULL: no 2D3D correction tally for this problem
         a = np.ascontiguousarray(arrays[name], dtype=_NP[ct]).reshape(-1)
         if a.size == 0:
             a = np.zeros(1, dtype=_NP[ct])
@@ -119,6 +123,8 @@ def load_library(path=None):
     lib.mocb200_get_boundary.argtypes = [H, C.c_int, C.c_int, C.c_int, _f64p]
     lib.mocb200_sweep.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.mocb200_get_coarse.argtypes = [H, C.c_int, _f64p, _f64p]
+    lib.mocb200_set_sn_xs.argtypes = [H, C.c_int, C.c_int, _f64p]
+    lib.mocb200_get_corrections.argtypes = [H, C.c_int, _f64p, _f64p]
     lib.mocb200_get_stats.argtypes = [H, C.POINTER(Stats)]
     lib.mocb200_last_sweep_ms.argtypes = [H, _f64p]
     lib.mocb200_set_timing.argtypes = [H, C.c_int]
@@ -232,6 +238,22 @@ class Sweeper:
         sf = np.zeros(self.n_surf)
         self._ck(self.lib.mocb200_get_coarse(self.h, group, _ptr(cur), _ptr(sf)), "get_coarse")
         return cur, sf
+
+    def set_sn_xs(self, g_begin, xs):
+        n = self.n_plane * int(self.problem.n_cell_plane)
+        xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(-1, n)
+        self._ck(self.lib.mocb200_set_sn_xs(self.h, g_begin, xs.shape[0], _ptr(xs)), "set_sn_xs")
+
+    def get_corrections(self, group, alpha=None, beta=None):
+        """alpha [2*n_ang, n_cell_total, 2], beta [2*n_ang, n_cell_total] of the last corrections sweep."""
+        n_ang2 = 2 * int(self.problem.n_ang)
+        n = self.n_plane * int(self.problem.n_cell_plane)
+        if alpha is None:
+            alpha = np.full((n_ang2, n, 2), np.nan)
+        if beta is None:
+            beta = np.full((n_ang2, n), np.nan)
+        self._ck(self.lib.mocb200_get_corrections(self.h, group, _ptr(alpha), _ptr(beta)), "get_corrections")
+        return alpha, beta
 
     def stats(self):
         s = Stats()

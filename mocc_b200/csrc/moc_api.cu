@@ -11,8 +11,7 @@
 #include <vector>
 
 #include "moc_kernels.cuh"
-#include "moc_track_kernel.cuh"
-#include "moc_cached_kernel.cuh"
+#include "moc_sweep_kernel.cuh"
 
 using namespace mocb200;
 
@@ -84,6 +83,18 @@ struct mocb200_sweeper {
     int cache_layout = 0; // 0 = no cache allocated, 1 = group-major (GL 1), 8 = group-fastest (GL 8)
     std::vector<bool> cache_valid; // per group
     double *d_qg = nullptr, *d_tg = nullptr; // group-major q-bar / tally [G][n_reg]
+    // 2D3D correction factors
+    bool have_corr = false;
+    std::vector<bool> have_sn_xs;
+    int n_cell_plane = 0, n_geom = 0;
+    int32_t *d_all_planes = nullptr; // macroplanes of this handle
+    int32_t *d_plane_unique = nullptr, *d_plane_cell_offset = nullptr, *d_uniq_reg_begin = nullptr;
+    int32_t *d_cell_fsr_begin = nullptr, *d_cell_fsr = nullptr, *d_ang_geom = nullptr, *d_coarse_surf = nullptr;
+    double *d_geom_len = nullptr, *d_area_x = nullptr, *d_area_y = nullptr, *d_ox = nullptr, *d_cell_dx = nullptr,
+           *d_cell_dy = nullptr, *d_sn_xs = nullptr;
+    double *d_dsum = nullptr, *d_ssum = nullptr, *d_alpha = nullptr, *d_beta = nullptr;
+    size_t dsum_elems = 0, ssum_elems = 0, corr_groups = 0;
+    int corr_g_begin = 0, corr_g_count = 0; // groups the alpha/beta buffers currently hold
     std::vector<TrackList> tlists;
     double *d_pseg_len = nullptr; // segment arrays with every track padded to a multiple of 4
     int32_t *d_pseg_fsr = nullptr;
@@ -438,7 +449,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                                      [](const TrackUnit &x, const TrackUnit &y) { return x.nseg > y.nseg; });
                     TrackList tl;
                     for (auto &tu : units) {
-                        tu.pad0 = (int32_t)tl.pseg;
+                        tu.cpos = (int32_t)tl.pseg;
                         tl.pseg += (tu.nseg + 3) & ~3;
                     }
                     tl.unique = u, tl.phase = phase, tl.np = np;
@@ -458,9 +469,96 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
         }
         h->track_grid       = h->sm_count;
         h->scratch_per_warp = (h->max_nseg / 16 + 1) * 8 * kMaxPolar;
-        const size_t n_sc   = (size_t)h->track_grid * (kTrackBlock / 32) * h->scratch_per_warp;
+        const size_t n_sc   = (size_t)h->track_grid * (kWarpBlock / 32) * h->scratch_per_warp;
         if ((rc2 = dev_alloc(h, &h->d_scratch, n_sc)))
             return rc2;
+    }
+
+    // ---- 2D3D correction-factor tables ----
+    h->n_cell_plane = p.n_cell_plane, h->n_geom = p.n_geom;
+    h->have_sn_xs.assign(p.n_group, false);
+    if (p.ang_area_x && p.ang_area_y && p.ang_ox && p.cell_dx && p.cell_dy) {
+        int rc3;
+        // FSRs of every unique plane, their coarse cell (as the ray data attributes segments to cells,
+        // correction_worker.hpp:145-162) and the path length of every geometry class through every FSR
+        std::vector<int32_t> uniq_reg_begin(p.n_unique + 1, 0);
+        std::vector<int> nreg_u(p.n_unique, 0);
+        for (int u = 0; u < p.n_unique; u++) {
+            int mx = -1;
+            for (int gi = 0; gi < p.n_geom; gi++)
+                for (int64_t t = p.geom_trk_begin[(size_t)u * p.n_geom + gi]; t < p.geom_trk_begin[(size_t)u * p.n_geom + gi + 1]; t++)
+                    for (int64_t sidx = p.trk_seg_begin[t]; sidx < p.trk_seg_begin[t + 1]; sidx++)
+                        mx = std::max(mx, (int)p.seg_fsr[sidx]);
+            nreg_u[u]             = mx + 1;
+            uniq_reg_begin[u + 1] = uniq_reg_begin[u] + nreg_u[u];
+        }
+        std::vector<int32_t> fsr_cell(uniq_reg_begin[p.n_unique], -1);
+        std::vector<double> geom_len((size_t)uniq_reg_begin[p.n_unique] * p.n_geom, 0.0);
+        for (int u = 0; u < p.n_unique; u++) {
+            for (int gi = 0; gi < p.n_geom; gi++) {
+                double *L = geom_len.data() + (size_t)uniq_reg_begin[u] * p.n_geom + (size_t)gi * nreg_u[u];
+                for (int64_t t = p.geom_trk_begin[(size_t)u * p.n_geom + gi]; t < p.geom_trk_begin[(size_t)u * p.n_geom + gi + 1]; t++) {
+                    const int64_t s0 = p.trk_seg_begin[t];
+                    const int nseg   = (int)(p.trk_seg_begin[t + 1] - s0);
+                    for (int k = 0; k < nseg; k++)
+                        L[p.seg_fsr[s0 + k]] += p.seg_len[s0 + k];
+                    int cell = p.trk_cm_start[4 * t + 0], iseg = 0;
+                    for (int64_t k = p.trk_cm_begin[t]; k < p.trk_cm_begin[t + 1]; k++) {
+                        const uint32_t c = p.cm_data[k];
+                        const int s_fw = c & 0xF, n_fw = (c >> 8) & 0xFF;
+                        if (s_fw != 7) {
+                            for (int i = 0; i < n_fw; i++, iseg++) {
+                                int32_t &fc = fsr_cell[uniq_reg_begin[u] + p.seg_fsr[s0 + iseg]];
+                                if (fc >= 0 && fc != cell)
+                                    return fail(h, MOCB200_ERR_INVALID, "FSR attributed to two coarse cells");
+                                fc = cell;
+                            }
+                        }
+                        if (s_fw < 4) {
+                            const int nb = p.coarse_nbr[4 * cell + s_fw];
+                            cell         = nb < 0 ? cell : nb;
+                        }
+                    }
+                }
+            }
+        }
+        std::vector<int32_t> cell_fsr_begin((size_t)p.n_unique * (p.n_cell_plane + 1), 0), cell_fsr(fsr_cell.size(), 0);
+        for (int u = 0; u < p.n_unique; u++) {
+            int32_t *cb = cell_fsr_begin.data() + (size_t)u * (p.n_cell_plane + 1);
+            for (int r = 0; r < nreg_u[u]; r++) {
+                const int c = fsr_cell[uniq_reg_begin[u] + r];
+                if (c < 0 || c >= p.n_cell_plane)
+                    return fail(h, MOCB200_ERR_INVALID, "FSR %d of unique plane %d is crossed by no ray", r, u);
+                cb[c + 1]++;
+            }
+            for (int c = 0; c < p.n_cell_plane; c++)
+                cb[c + 1] += cb[c];
+            std::vector<int32_t> fill(cb, cb + p.n_cell_plane);
+            for (int r = 0; r < nreg_u[u]; r++)
+                cell_fsr[uniq_reg_begin[u] + fill[fsr_cell[uniq_reg_begin[u] + r]]++] = r;
+        }
+        std::vector<int32_t> all_planes;
+        for (int ip = h->plane_begin; ip < h->plane_end; ip++)
+            all_planes.push_back(ip);
+        if ((rc3 = dev_upload(h, &h->d_all_planes, all_planes)) ||
+            (rc3 = dev_upload(h, &h->d_plane_unique, p.plane_unique, (size_t)p.n_plane)) ||
+            (rc3 = dev_upload(h, &h->d_plane_cell_offset, p.plane_cell_offset, (size_t)p.n_plane)) ||
+            (rc3 = dev_upload(h, &h->d_uniq_reg_begin, uniq_reg_begin)) ||
+            (rc3 = dev_upload(h, &h->d_cell_fsr_begin, cell_fsr_begin)) || (rc3 = dev_upload(h, &h->d_cell_fsr, cell_fsr)) ||
+            (rc3 = dev_upload(h, &h->d_geom_len, geom_len)) ||
+            (rc3 = dev_upload(h, &h->d_ang_geom, p.ang_geom, (size_t)p.n_ang)) ||
+            (rc3 = dev_upload(h, &h->d_coarse_surf, p.coarse_surf, (size_t)4 * p.n_cell_plane)) ||
+            (rc3 = dev_upload(h, &h->d_area_x, p.ang_area_x, (size_t)p.n_ang)) ||
+            (rc3 = dev_upload(h, &h->d_area_y, p.ang_area_y, (size_t)p.n_ang)) ||
+            (rc3 = dev_upload(h, &h->d_ox, p.ang_ox, (size_t)p.n_ang)) ||
+            (rc3 = dev_upload(h, &h->d_cell_dx, p.cell_dx, (size_t)p.n_cell_plane)) ||
+            (rc3 = dev_upload(h, &h->d_cell_dy, p.cell_dy, (size_t)p.n_cell_plane)))
+            return rc3;
+        const size_t nsx = (size_t)p.n_plane * p.n_cell_plane * h->GP;
+        if ((rc3 = dev_alloc(h, &h->d_sn_xs, nsx)))
+            return rc3;
+        CUDA_TRY(h, cudaMemset(h->d_sn_xs, 0, nsx * sizeof(double)));
+        h->have_corr = true;
     }
 
     // ---- uploads ----
@@ -524,7 +622,8 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     CUDA_TRY(h, cudaMemset(h->d_current, 0, nsf * sizeof(double)));
     CUDA_TRY(h, cudaMemset(h->d_surfflux, 0, nsf * sizeof(double)));
 
-    h->stage_elems = std::max<size_t>({(size_t)p.n_reg, (size_t)p.bc_per_group, (size_t)p.n_surf}) * p.n_group;
+    h->stage_elems = std::max<size_t>({(size_t)p.n_reg, (size_t)p.bc_per_group, (size_t)p.n_surf,
+                                       (size_t)p.n_plane * p.n_cell_plane}) * p.n_group;
     if ((rc = dev_alloc(h, &h->d_stage, h->stage_elems)))
         return rc;
     CUDA_TRY(h, cudaMallocHost((void **)&h->h_stage, h->stage_elems * sizeof(double)));
@@ -569,48 +668,32 @@ SweepFn pick_kernel(int np, int tally)
     return nullptr;
 }
 
-typedef void (*TrackFn)(const TrackArgs);
+typedef void (*WarpFn)(const WarpArgs);
 
-template <int GL> TrackFn pick_track_gl(int np, int tally)
+template <int GL, bool CACHED> WarpFn pick_warp_gl(int np, int tally)
 {
-    switch (np * 2 + (tally ? 1 : 0)) {
-    case 2: return sweep_track_kernel<GL, 1, 4, 0>;
-    case 3: return sweep_track_kernel<GL, 1, 4, 1>;
-    case 4: return sweep_track_kernel<GL, 2, 4, 0>;
-    case 5: return sweep_track_kernel<GL, 2, 4, 1>;
-    case 6: return sweep_track_kernel<GL, 3, 4, 0>;
-    case 7: return sweep_track_kernel<GL, 3, 4, 1>;
-    case 8: return sweep_track_kernel<GL, 4, 4, 0>;
-    case 9: return sweep_track_kernel<GL, 4, 4, 1>;
+    switch (np * 3 + tally) {
+    case 3: return sweep_warp_kernel<GL, 1, 0, CACHED>;
+    case 4: return sweep_warp_kernel<GL, 1, 1, CACHED>;
+    case 5: return sweep_warp_kernel<GL, 1, 2, CACHED>;
+    case 6: return sweep_warp_kernel<GL, 2, 0, CACHED>;
+    case 7: return sweep_warp_kernel<GL, 2, 1, CACHED>;
+    case 8: return sweep_warp_kernel<GL, 2, 2, CACHED>;
+    case 9: return sweep_warp_kernel<GL, 3, 0, CACHED>;
+    case 10: return sweep_warp_kernel<GL, 3, 1, CACHED>;
+    case 11: return sweep_warp_kernel<GL, 3, 2, CACHED>;
+    case 12: return sweep_warp_kernel<GL, 4, 0, CACHED>;
+    case 13: return sweep_warp_kernel<GL, 4, 1, CACHED>;
+    case 14: return sweep_warp_kernel<GL, 4, 2, CACHED>;
     }
     return nullptr;
 }
 
-TrackFn pick_track_kernel(int gl, int np, int tally)
+WarpFn pick_warp_kernel(int gl, int np, int tally, bool cached)
 {
-    return gl == 1 ? pick_track_gl<1>(np, tally) : pick_track_gl<8>(np, tally);
-}
-
-typedef void (*CachedFn)(const CachedArgs);
-
-template <int GL> CachedFn pick_cached_gl(int np, int tally)
-{
-    switch (np * 2 + (tally ? 1 : 0)) {
-    case 2: return sweep_cached_kernel<GL, 1, 0>;
-    case 3: return sweep_cached_kernel<GL, 1, 1>;
-    case 4: return sweep_cached_kernel<GL, 2, 0>;
-    case 5: return sweep_cached_kernel<GL, 2, 1>;
-    case 6: return sweep_cached_kernel<GL, 3, 0>;
-    case 7: return sweep_cached_kernel<GL, 3, 1>;
-    case 8: return sweep_cached_kernel<GL, 4, 0>;
-    case 9: return sweep_cached_kernel<GL, 4, 1>;
-    }
-    return nullptr;
-}
-
-CachedFn pick_cached_kernel(int gl, int np, int tally)
-{
-    return gl == 1 ? pick_cached_gl<1>(np, tally) : pick_cached_gl<8>(np, tally);
+    if (cached)
+        return gl == 1 ? pick_warp_gl<1, true>(np, tally) : pick_warp_gl<8, true>(np, tally);
+    return gl == 1 ? pick_warp_gl<1, false>(np, tally) : pick_warp_gl<8, false>(np, tally);
 }
 
 int track_smem_bytes(const mocb200_sweeper *h)
@@ -729,8 +812,8 @@ int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb
     }
     for (int gl = 1; gl <= 8; gl *= 8)
         for (int np = 1; np <= kMaxPolar; np++)
-            for (int t = 0; t < 2; t++) {
-                e = cudaFuncSetAttribute((const void *)pick_track_kernel(gl, np, t),
+            for (int t = 0; t < 3; t++) {
+                e = cudaFuncSetAttribute((const void *)pick_warp_kernel(gl, np, t, false),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, track_smem_bytes(h));
                 if (e != cudaSuccess) {
                     fail(nullptr, MOCB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -754,6 +837,9 @@ int mocb200_destroy(mocb200_sweeper *h)
     for (auto &tl : h->tlists)
         if (tl.d_cache)
             cudaFree(tl.d_cache);
+    for (double *q : {h->d_dsum, h->d_ssum, h->d_alpha, h->d_beta})
+        if (q)
+            cudaFree(q);
     if (h->h_stage)
         cudaFreeHost(h->h_stage);
     for (auto &pr : h->ev_pool) {
@@ -873,8 +959,17 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         return rc;
     if (n_inner < 1)
         return fail(h, MOCB200_ERR_INVALID, "n_inner must be >= 1");
-    if (tally_mode != MOCB200_TALLY_NONE && tally_mode != MOCB200_TALLY_CURRENT)
-        return fail(h, MOCB200_ERR_INVALID, "tally mode %d not available", tally_mode);
+    if (tally_mode < MOCB200_TALLY_NONE || tally_mode > MOCB200_TALLY_CORRECTIONS)
+        return fail(h, MOCB200_ERR_INVALID, "unknown tally mode %d", tally_mode);
+    if (tally_mode == MOCB200_TALLY_CORRECTIONS) {
+        if (h->kernel == MOCB200_KERNEL_ITEM)
+            return fail(h, MOCB200_ERR_INVALID, "the item kernel has no correction-factor tally");
+        if (!h->have_corr)
+            return fail(h, MOCB200_ERR_STATE, "problem was created without the 2D3D correction tables");
+        for (int g = g_begin; g < g_begin + g_count; g++)
+            if (!h->have_sn_xs[g])
+                return fail(h, MOCB200_ERR_STATE, "mocb200_set_sn_xs has not been called for group %d", g);
+    }
     for (int g = g_begin; g < g_begin + g_count; g++)
         if (!h->have_xs[g])
             return fail(h, MOCB200_ERR_STATE, "mocb200_set_xs has not been called for group %d", g);
@@ -917,7 +1012,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 c.planes = tl.d_planes, c.n_planes = tl.n_planes;
                 c.seg_len = h->d_pseg_len, c.seg_fsr = h->d_pseg_fsr, c.ang_rsintheta = h->d_rsin;
                 c.plane_first_reg = h->d_plane_first_reg, c.xstr = h->d_xstr;
-                c.g_begin = g_begin, c.g_count = g_count, c.g_cache_begin = 0, c.g_cache_count = h->G;
+                c.g_begin = g_begin, c.g_count = g_count, c.cache_groups = h->G;
                 c.GP = h->GP, c.np = tl.np, c.group_major = gl == 1 ? 1 : 0;
                 c.cache = tl.d_cache, c.list_pseg = tl.pseg;
                 c.exp_table = h->d_exp, c.exp_n = h->exp_n, c.exp_min = h->exp_min, c.exp_max = h->exp_max;
@@ -931,26 +1026,47 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         }
     }
 
+    if (tally_mode == MOCB200_TALLY_CORRECTIONS) {
+        // per-angle, per-direction sums of the corrections sweep and the resulting factors
+        const size_t ngl = gl == 1 ? (size_t)g_count : (size_t)h->GP;
+        const size_t nd  = (size_t)h->n_reg * 2 * h->n_ang * ngl;
+        const size_t ns  = (size_t)h->n_plane * h->n_ang * h->n_surf_plane * 2 * ngl;
+        if (nd > h->dsum_elems || ns > h->ssum_elems || (size_t)g_count > h->corr_groups) {
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            for (double **q : {&h->d_dsum, &h->d_ssum, &h->d_alpha, &h->d_beta})
+                if (*q) {
+                    CUDA_TRY(h, cudaFree(*q));
+                    *q = nullptr;
+                }
+            const size_t nc = (size_t)g_count * 2 * h->n_ang * h->n_plane * h->n_cell_plane;
+            CUDA_TRY(h, cudaMalloc((void **)&h->d_dsum, nd * sizeof(double)));
+            CUDA_TRY(h, cudaMalloc((void **)&h->d_ssum, ns * sizeof(double)));
+            CUDA_TRY(h, cudaMalloc((void **)&h->d_alpha, 2 * nc * sizeof(double)));
+            CUDA_TRY(h, cudaMalloc((void **)&h->d_beta, nc * sizeof(double)));
+            h->dsum_elems = nd, h->ssum_elems = ns, h->corr_groups = (size_t)g_count;
+        }
+    }
+
     for (int inner = 0; inner < n_inner; inner++) {
         const bool last = inner == n_inner - 1;
         const int tally = last ? tally_mode : MOCB200_TALLY_NONE;
+        if (tally == MOCB200_TALLY_CORRECTIONS) {
+            CUDA_TRY(h, cudaMemsetAsync(h->d_dsum, 0, h->dsum_elems * sizeof(double), h->stream));
+            CUDA_TRY(h, cudaMemsetAsync(h->d_ssum, 0, h->ssum_elems * sizeof(double), h->stream));
+        }
         // q-bar and tally reset (whole FSR range: cheap, keeps indexing simple)
         const int ss_grid = grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count);
-        if (cached)
-            self_scatter_q_kernel<<<ss_grid, 256, 0, h->stream>>>(
-                h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_qbar,
-                group_major ? h->d_qg : h->d_qbar, group_major ? h->d_tg : h->d_tally, group_major ? 1 : 0,
-                use_qbar ? 0 : 1);
-        else if (h->kernel == MOCB200_KERNEL_TRACK)
-            self_scatter_xq_kernel<<<ss_grid, 256, 0, h->stream>>>(
-                h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_xstr,
-                h->d_qbar, h->d_xq, h->d_qbar, h->d_tally, use_qbar ? 0 : 1);
-        else
+        if (h->kernel == MOCB200_KERNEL_ITEM)
             self_scatter_kernel<<<ss_grid, 256, 0, h->stream>>>(
                 h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_qbar,
                 h->d_tally, use_qbar ? 0 : 1);
+        else
+            self_scatter_q_kernel<<<ss_grid, 256, 0, h->stream>>>(
+                h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_xstr,
+                h->d_qbar, group_major ? h->d_qg : h->d_qbar, cached ? nullptr : h->d_xq,
+                group_major ? h->d_tg : h->d_tally, group_major ? 1 : 0, use_qbar ? 0 : 1);
         h->stats.kernel_launches++;
-        if (tally == MOCB200_TALLY_CURRENT) {
+        if (tally != MOCB200_TALLY_NONE) {
             zero_groups_kernel<<<grid_for((int64_t)h->n_surf * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
                 h->n_surf, h->GP, g_begin, g_count, h->d_current);
             zero_groups_kernel<<<grid_for((int64_t)h->n_surf * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
@@ -1007,41 +1123,27 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 const int64_t warps = (int64_t)tl.n_units * tl.n_planes * n_gsets;
                 const int grid      = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 15) / 16, h->track_grid));
                 uint32_t *counter   = h->d_counters + h->lists.size() + il;
-                if (cached) {
-                    CachedArgs a{};
-                    a.units = tl.d_units, a.n_units = tl.n_units, a.counter = counter;
-                    a.bundles = h->d_bundles, a.planes = tl.d_planes, a.n_planes = tl.n_planes;
-                    a.seg_fsr = h->d_pseg_fsr, a.xptr = h->d_xptr, a.cross = h->d_xcross;
-                    a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
-                    a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
-                    a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
-                    a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
-                    a.n_ang = h->n_ang, a.bc_per_group = h->bcpg;
-                    a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP, a.n_gsets = n_gsets, a.n_reg = h->n_reg;
-                    a.q = group_major ? h->d_qg : h->d_qbar, a.tally = group_major ? h->d_tg : h->d_tally;
-                    a.bc_in = bc_in, a.bc_out = bc_out;
-                    a.current = h->d_current, a.surface_flux = h->d_surfflux;
-                    a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
-                    a.cache = tl.d_cache, a.list_pseg = tl.pseg, a.cache_groups = h->G;
-                    pick_cached_kernel(gl, tl.np, tally)<<<grid, kCachedBlock, 0, h->stream>>>(a);
-                } else {
-                    TrackArgs a{};
-                    a.units = tl.d_units, a.n_units = tl.n_units, a.counter = counter;
-                    a.bundles = h->d_bundles, a.planes = tl.d_planes, a.n_planes = tl.n_planes;
-                    a.seg_len = h->d_pseg_len, a.seg_fsr = h->d_pseg_fsr, a.xptr = h->d_xptr, a.cross = h->d_xcross;
-                    a.ang_rsintheta = h->d_rsin, a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
-                    a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
-                    a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
-                    a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
-                    a.n_ang = h->n_ang, a.bc_per_group = h->bcpg;
-                    a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP, a.n_gsets = n_gsets;
-                    a.xq = h->d_xq, a.tally = h->d_tally;
-                    a.bc_in = bc_in, a.bc_out = bc_out;
-                    a.current = h->d_current, a.surface_flux = h->d_surfflux;
-                    a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
-                    a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
-                    pick_track_kernel(gl, tl.np, tally)<<<grid, kTrackBlock, track_smem_bytes(h), h->stream>>>(a);
-                }
+                WarpArgs a{};
+                a.units = tl.d_units, a.n_units = tl.n_units, a.counter = counter;
+                a.bundles = h->d_bundles, a.planes = tl.d_planes, a.n_planes = tl.n_planes;
+                a.seg_len = h->d_pseg_len, a.seg_fsr = h->d_pseg_fsr, a.xptr = h->d_xptr, a.cross = h->d_xcross;
+                a.ang_rsintheta = h->d_rsin, a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
+                a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;
+                a.bc_dst_off = h->d_bc_dst_off, a.bc_dst_kind = h->d_bc_dst_kind;
+                a.plane_first_reg = h->d_plane_first_reg, a.plane_surf_offset = h->d_plane_surf_offset;
+                a.n_ang = h->n_ang, a.bc_per_group = h->bcpg, a.n_plane_total = h->n_plane;
+                a.n_surf_plane = h->n_surf_plane;
+                a.g_begin = g_begin, a.g_count = g_count, a.GP = h->GP, a.n_gsets = n_gsets, a.n_reg = h->n_reg;
+                a.xq = h->d_xq, a.q = group_major ? h->d_qg : h->d_qbar;
+                a.tally = group_major ? h->d_tg : h->d_tally;
+                a.bc_in = bc_in, a.bc_out = bc_out;
+                a.current = h->d_current, a.surface_flux = h->d_surfflux;
+                a.dsum = h->d_dsum, a.ssum = h->d_ssum;
+                a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
+                a.cache = tl.d_cache, a.list_pseg = tl.pseg, a.cache_groups = h->G;
+                a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
+                pick_warp_kernel(gl, tl.np, tally, cached)<<<grid, kWarpBlock, cached ? 0 : track_smem_bytes(h),
+                                                             h->stream>>>(a);
                 h->stats.kernel_launches++;
                 h->stats.sweep_launches++;
             }
@@ -1051,6 +1153,25 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         if (last) {
             CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
             h->ev_valid = true;
+        }
+        if (tally == MOCB200_TALLY_CORRECTIONS) {
+            CorrArgs c{};
+            c.planes = h->d_all_planes, c.n_planes = h->plane_end - h->plane_begin, c.n_ang = h->n_ang;
+            c.n_cell_plane = h->n_cell_plane, c.n_surf_plane = h->n_surf_plane, c.n_plane_total = h->n_plane;
+            c.n_geom = h->n_geom, c.GP = h->GP, c.n_reg = h->n_reg, c.gl = gl;
+            c.g_begin = g_begin, c.g_count = g_count;
+            c.plane_unique = h->d_plane_unique, c.plane_first_reg = h->d_plane_first_reg;
+            c.plane_cell_offset = h->d_plane_cell_offset, c.uniq_reg_begin = h->d_uniq_reg_begin;
+            c.cell_fsr_begin = h->d_cell_fsr_begin, c.cell_fsr = h->d_cell_fsr, c.geom_len = h->d_geom_len;
+            c.ang_geom = h->d_ang_geom, c.ang_rsintheta = h->d_rsin;
+            c.ang_area_x = h->d_area_x, c.ang_area_y = h->d_area_y, c.ang_ox = h->d_ox;
+            c.cell_dx = h->d_cell_dx, c.cell_dy = h->d_cell_dy, c.coarse_surf = h->d_coarse_surf;
+            c.xstr = h->d_xstr, c.xstr_true = h->d_xstr_src, c.qbar = h->d_qbar, c.sn_xs = h->d_sn_xs;
+            c.dsum = h->d_dsum, c.ssum = h->d_ssum, c.alpha = h->d_alpha, c.beta = h->d_beta;
+            const int64_t n = (int64_t)c.n_planes * c.n_ang * c.n_cell_plane * 2 * g_count;
+            corrections_kernel<<<grid_for(n, 128, h->sm_count), 128, 0, h->stream>>>(c);
+            h->stats.kernel_launches++;
+            h->corr_g_begin = g_begin, h->corr_g_count = g_count;
         }
         if (jacobi)
             h->bc_cur = 1 - h->bc_cur;
@@ -1074,6 +1195,50 @@ int mocb200_get_coarse(mocb200_sweeper *h, int group, double *current, double *s
     if ((rc = download_columns(h, current, h->n_surf, group, 1, h->d_current)))
         return rc;
     return download_columns(h, surface_flux, h->n_surf, group, 1, h->d_surfflux);
+}
+
+int mocb200_set_sn_xs(mocb200_sweeper *h, int g_begin, int g_count, const double *xs)
+{
+    int rc = check_groups(h, g_begin, g_count);
+    if (rc)
+        return rc;
+    if (!xs)
+        return fail(h, MOCB200_ERR_INVALID, "set_sn_xs: NULL array");
+    if (!h->have_corr)
+        return fail(h, MOCB200_ERR_STATE, "problem was created without the 2D3D correction tables");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if ((rc = upload_columns(h, xs, (int64_t)h->n_plane * h->n_cell_plane, g_begin, g_count, h->d_sn_xs)))
+        return rc;
+    for (int g = g_begin; g < g_begin + g_count; g++)
+        h->have_sn_xs[g] = true;
+    return MOCB200_OK;
+}
+
+int mocb200_get_corrections(mocb200_sweeper *h, int group, double *alpha, double *beta)
+{
+    int rc = check_groups(h, group, 1);
+    if (rc)
+        return rc;
+    if (!alpha || !beta)
+        return fail(h, MOCB200_ERR_INVALID, "get_corrections: NULL array");
+    if (!h->d_alpha || group < h->corr_g_begin || group >= h->corr_g_begin + h->corr_g_count)
+        return fail(h, MOCB200_ERR_STATE, "no correction factors of group %d on the device", group);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const size_t ncp    = (size_t)h->n_cell_plane;
+    const size_t n_cell = (size_t)h->n_plane * ncp;
+    const size_t grel   = (size_t)(group - h->corr_g_begin);
+    // only this handle's macroplanes: one contiguous cell range per angle
+    const size_t c0 = (size_t)h->plane_begin * ncp, cn = (size_t)(h->plane_end - h->plane_begin) * ncp;
+    for (int ia = 0; ia < 2 * h->n_ang; ia++) {
+        const size_t o = (grel * 2 * h->n_ang + ia) * n_cell + c0;
+        CUDA_TRY(h, cudaMemcpyAsync(alpha + 2 * ((size_t)ia * n_cell + c0), h->d_alpha + 2 * o, 2 * cn * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(beta + (size_t)ia * n_cell + c0, h->d_beta + o, cn * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return MOCB200_OK;
 }
 
 int mocb200_get_stats(const mocb200_sweeper *h, mocb200_stats *out)

@@ -1,6 +1,8 @@
 #include "cuda_moc_sweeper.hpp"
 
 #include <algorithm>
+#include <array>
+#include <cmath>
 #include <sstream>
 
 #include "core/coarse_data.hpp"
@@ -28,9 +30,13 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
     opt.device              = cu.attribute("device").as_int(0);
     opt.max_polar           = cu.attribute("max_polar").as_int(0);
     group_batch_            = cu.attribute("group_batch").as_bool(false);
-    std::string kernel      = cu.attribute("kernel").as_string("track");
-    if (kernel == "track")
+    std::string kernel      = cu.attribute("kernel").as_string("auto");
+    if (kernel == "auto")
+        opt.kernel = MOCB200_KERNEL_AUTO;
+    else if (kernel == "track")
         opt.kernel = MOCB200_KERNEL_TRACK;
+    else if (kernel == "cached")
+        opt.kernel = MOCB200_KERNEL_CACHED;
     else if (kernel == "item")
         opt.kernel = MOCB200_KERNEL_ITEM;
     else
@@ -43,7 +49,8 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
     std::vector<double> vol(vol_.begin(), vol_.end());
     FlatProblem fp = flatten(mesh_, rays_, macroplane_unique_ids_, first_reg_macroplane_, vol.data(), (int)n_reg_,
                              (int)n_group_);
-    n_bc_ = fp.bc_per_group;
+    n_bc_            = fp.bc_per_group;
+    plane_xs_offset_ = fp.plane_xs_offset;
     if (n_bc_ * (int)n_group_ != boundary_[0].size())
         throw EXCEPT("Flattened boundary layout does not match BoundaryCondition storage.");
     mocb200_problem prob = fp.view();
@@ -124,16 +131,21 @@ void CudaMoCSweeper::upload_group(int group)
               "mocb200_set_boundary");
 }
 
-// Device results of one group -> host objects the rest of MOCC reads.
-void CudaMoCSweeper::download_group(int group, int tally)
+void CudaMoCSweeper::download_flux(int group)
 {
     check(mocb200_get_flux(dev_, group, 1, col_.data()), "mocb200_get_flux");
     for (int ireg = 0; ireg < (int)n_reg_; ireg++)
         flux_(ireg, group) = col_[ireg];
+}
+
+// Device results of one group -> host objects the rest of MOCC reads.
+void CudaMoCSweeper::download_group(int group, int tally)
+{
+    download_flux(group);
     for (int ip = 0; ip < n_macroplane_; ip++)
         check(mocb200_get_boundary(dev_, ip, group, 1, boundary_[ip].get_boundary(group, 0).second),
               "mocb200_get_boundary");
-    if (tally == MOCB200_TALLY_CURRENT) {
+    if (tally != MOCB200_TALLY_NONE) {
         // moc_sweeper.cpp:208-215: zero the radial data, tally, flag; the raw device tallies
         // then go through the reference's own post_sweep (sub-plane expansion and division
         // by the surface area, moc_current_worker.hpp:272-318) so every quirk is kept.
@@ -150,7 +162,7 @@ void CudaMoCSweeper::download_group(int group, int tally)
         cw.post_sweep();
         coarse_data_->set_has_radial_data(true);
     }
-    post_group(group);
+    post_group(group, tally);
 }
 
 void CudaMoCSweeper::sweep(int group)
@@ -162,22 +174,148 @@ void CudaMoCSweeper::sweep(int group)
     flux_1g_.reference(flux_(blitz::Range::all(), group));
     upload_group(group);
     const int tally = tally_mode();
-    if (!group_batch_) {
-        check(mocb200_sweep(dev_, group, 1, (int)n_inner_, tally, 0), "mocb200_sweep");
-        download_group(group, tally);
+    auto run = [&](int g0, int gc) {
         double ms = 0.0;
+        if (split_last_inner() && tally != MOCB200_TALLY_NONE) {
+            // the host refreshes data between the plain inners and the tallying one
+            if (n_inner_ > 1) {
+                check(mocb200_sweep(dev_, g0, gc, (int)n_inner_ - 1, MOCB200_TALLY_NONE, 0), "mocb200_sweep");
+                for (int ig = g0; ig < g0 + gc; ig++)
+                    download_flux(ig);
+            }
+            for (int ig = g0; ig < g0 + gc; ig++)
+                before_last_inner(ig);
+            check(mocb200_sweep(dev_, g0, gc, 1, tally, 0), "mocb200_sweep");
+        } else {
+            check(mocb200_sweep(dev_, g0, gc, (int)n_inner_, tally, 0), "mocb200_sweep");
+        }
+        for (int ig = g0; ig < g0 + gc; ig++)
+            download_group(ig, tally);
         if (mocb200_last_sweep_ms(dev_, &ms) == MOCB200_OK)
             device_sweep_ms_ += ms * n_inner_; // last inner timed; inners are alike
-    } else if (group == (int)n_group_ - 1) {
-        check(mocb200_sweep(dev_, 0, (int)n_group_, (int)n_inner_, tally, 0), "mocb200_sweep");
-        for (int ig = 0; ig < (int)n_group_; ig++)
-            download_group(ig, tally);
-        double ms = 0.0;
-        if (mocb200_last_sweep_ms(dev_, &ms) == MOCB200_OK)
-            device_sweep_ms_ += ms * n_inner_;
-    }
+    };
+    if (!group_batch_)
+        run(group, 1);
+    else if (group == (int)n_group_ - 1)
+        run(0, (int)n_group_);
 
     timer_.toc();
     timer_sweep_.toc();
+}
+
+// ---------------------------------------------------------------------------------------------
+CudaMoCSweeper2D3D::CudaMoCSweeper2D3D(const pugi::xml_node &input, const CoreMesh &mesh)
+    : CudaMoCSweeper(input, mesh), correction_residuals_(n_group_)
+{
+    LogFile << "Constructing the B200 (CUDA) 2D3D MoC sweeper" << std::endl;
+    const size_t n_cell = (size_t)n_macroplane_ * mesh_.nx() * mesh_.ny();
+    sn_col_.resize(n_cell);
+    alpha_.resize(n_cell * ang_quad_.ndir() / 2 * 2);
+    beta_.resize(n_cell * ang_quad_.ndir() / 2);
+}
+
+void CudaMoCSweeper2D3D::set_coupling(std::shared_ptr<CorrectionData> data, SP_XSMeshHomogenized_t xsmesh,
+                                      ExpandedXS &xstr)
+{
+    if (corrections_ || sn_xs_mesh_)
+        throw EXCEPT("Correction data already assigned.");
+    corrections_ = data;
+    sn_xs_mesh_  = xsmesh;
+    xstr_sn_     = xstr;
+}
+
+void CudaMoCSweeper2D3D::set_self_coupling()
+{
+    internal_coupling_ = true;
+    corrections_ =
+        std::shared_ptr<CorrectionData>(new CorrectionData(mesh_, ang_quad_.ndir() / 2, xs_mesh_->n_group()));
+    sn_xs_mesh_ = this->get_homogenized_xsmesh();
+    sn_xs_mesh_->set_flux(flux_);
+    xstr_sn_ = ExpandedXS(sn_xs_mesh_.get());
+}
+
+void CudaMoCSweeper2D3D::sweep(int group)
+{
+    assert(sn_xs_mesh_);
+    if (!coarse_data_)
+        throw EXCEPT("2D3D MoC sweeper needs coarse data to collect "
+                     "calculate correction factors. Try enabling CMFD.");
+    n_sweep_++;
+    n_sweep_inner_ += n_inner_;
+    CudaMoCSweeper::sweep(group);
+}
+
+// moc_sweeper_2d3d.cpp:85-88: right before the tallying inner the Sn mesh is re-homogenised with the
+// current scalar flux; beta divides by that homogenised XS (correction_worker.cpp:84-93).
+void CudaMoCSweeper2D3D::before_last_inner(int group)
+{
+    if (group == 0 || !group_batch_)
+        sn_xs_mesh_->update();
+    xstr_sn_.expand(group);
+    const int ncp = mesh_.nx() * mesh_.ny();
+    for (int ip = 0; ip < n_macroplane_; ip++)
+        for (int ic = 0; ic < ncp; ic++)
+            sn_col_[(size_t)ip * ncp + ic] = xstr_sn_[ic + plane_xs_offset_[ip]];
+    check(mocb200_set_sn_xs(dev_, group, 1, sn_col_.data()), "mocb200_set_sn_xs");
+}
+
+// Device correction factors -> CorrectionData, with the residual bookkeeping of
+// calculate_corrections (correction_worker.cpp:112-151) in the reference's plane/angle/cell order.
+void CudaMoCSweeper2D3D::post_group(int group, int tally)
+{
+    if (tally != MOCB200_TALLY_CORRECTIONS)
+        return;
+    check(mocb200_get_corrections(dev_, group, alpha_.data(), beta_.data()), "mocb200_get_corrections");
+    const int ncp       = mesh_.nx() * mesh_.ny();
+    const size_t n_cell = (size_t)n_macroplane_ * ncp;
+    const int n_ang     = ang_quad_.ndir() / 4; // sweep angles (octants 1-2)
+    std::array<real_t, 3> resid = {{0.0, 0.0, 0.0}};
+    for (int ip = 0; ip < n_macroplane_; ip++) {
+        const int cell_offset = mesh_.coarse_cell_offset(ip);
+        for (int a = 0; a < n_ang; a++) {
+            for (int ic = 0; ic < ncp; ic++) {
+                const int icc = ic + cell_offset;
+                for (int iang : {a, (int)ang_quad_.reverse(a)}) {
+                    const real_t ax = alpha_[((size_t)iang * n_cell + icc) * 2 + 0];
+                    const real_t ay = alpha_[((size_t)iang * n_cell + icc) * 2 + 1];
+                    const real_t b  = beta_[(size_t)iang * n_cell + icc];
+                    real_t e        = ax - corrections_->alpha(icc, iang, group, Normal::X_NORM);
+                    resid[0] += e * e;
+                    e = ay - corrections_->alpha(icc, iang, group, Normal::Y_NORM);
+                    resid[1] += e * e;
+                    e = b - corrections_->beta(icc, iang, group);
+                    resid[2] += e * e;
+                    corrections_->alpha(icc, iang, group, Normal::X_NORM) = ax;
+                    corrections_->alpha(icc, iang, group, Normal::Y_NORM) = ay;
+                    corrections_->beta(icc, iang, group)                  = b;
+                }
+            }
+        }
+    }
+    correction_residuals_[group].push_back({{std::sqrt(resid[0]), std::sqrt(resid[1]), std::sqrt(resid[2])}});
+}
+
+void CudaMoCSweeper2D3D::output(H5Node &node) const
+{
+    LogFile << "MoC Sweeper 2D3D (B200) output:" << std::endl;
+    LogFile << "    Number of sweeps, outer: " << n_sweep_ << std::endl;
+    LogFile << "    Number of sweeps, inner: " << n_sweep_inner_ << std::endl;
+    MoCSweeper::output(node);
+    if (internal_coupling_) {
+        corrections_->output(node);
+        sn_xs_mesh_->update();
+        sn_xs_mesh_->output(node);
+    }
+    auto residual_group = node.create_group("correction_residual");
+    for (int ig = 0; ig < (int)n_group_; ig++) {
+        auto g = residual_group.create_group(std::to_string(ig + 1));
+        VecF ax, ay, b;
+        for (const auto &d : correction_residuals_[ig]) {
+            ax.push_back(d[0]), ay.push_back(d[1]), b.push_back(d[2]);
+        }
+        g.write("alpha_x", ax);
+        g.write("alpha_y", ay);
+        g.write("beta", b);
+    }
 }
 }

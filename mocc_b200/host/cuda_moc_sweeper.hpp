@@ -27,6 +27,8 @@
 #include "core/core_mesh.hpp"
 #include "sweepers/moc/moc_sweeper.hpp"
 
+#include "sweepers/cmdo/correction_data.hpp"
+
 #include "mocc_b200.h"
 
 namespace mocc_b200 {
@@ -51,11 +53,22 @@ protected:
     {
         return coarse_data_ ? MOCB200_TALLY_CURRENT : MOCB200_TALLY_NONE;
     }
-    // Hook called after the device results of `group` are back on the host
-    virtual void post_group(int group)
+    // Hook between the first n_inner-1 inners and the last one (2D3D refreshes the Sn cross sections there)
+    virtual bool split_last_inner() const
+    {
+        return false;
+    }
+    virtual void before_last_inner(int group)
     {
         (void)group;
     }
+    // Hook called after the device results of `group` are back on the host
+    virtual void post_group(int group, int tally)
+    {
+        (void)group;
+        (void)tally;
+    }
+    void download_flux(int group);
 
     void check(int rc, const char *what) const;
     void upload_group(int group);
@@ -69,8 +82,46 @@ protected:
     std::vector<double> xstr_true_fsr_; // un-split transport XS (source normalisation)
     std::vector<double> xs_self_fsr_;   // within-group scattering
     std::vector<bool> xs_uploaded_;
+    std::vector<int> plane_xs_offset_; // CurrentCorrections::mplane_offset_
     std::vector<double> col_, cur_, sflux_;
     double device_sweep_ms_ = 0.0;
     mocb200_stats stats_{};
+};
+
+// The per-plane MoC sweeper of the 2D3D method on the B200: same interface as
+// cmdo::MoCSweeper_2D3D (src/sweepers/cmdo/moc_sweeper_2d3d.hpp:25-88), so that the reference's
+// PlaneSweeper_2D3D can hold it in place of the CPU class (plane_sweeper_2d3d_cuda.cpp).
+// The last inner iteration of every sweep(group) tallies coarse currents AND the CDD correction
+// factors alpha/beta (cmdo::CurrentCorrections, correction_worker.hpp:36-290) on the device.
+class CudaMoCSweeper2D3D : public CudaMoCSweeper {
+public:
+    CudaMoCSweeper2D3D(const pugi::xml_node &input, const mocc::CoreMesh &mesh);
+
+    void sweep(int group) override;
+
+    void set_coupling(std::shared_ptr<mocc::CorrectionData> data, mocc::SP_XSMeshHomogenized_t xsmesh,
+                      mocc::ExpandedXS &xstr);
+    void set_self_coupling();
+    void output(mocc::H5Node &node) const override;
+
+protected:
+    int tally_mode() const override
+    {
+        return MOCB200_TALLY_CORRECTIONS;
+    }
+    bool split_last_inner() const override
+    {
+        return true;
+    }
+    void before_last_inner(int group) override;
+    void post_group(int group, int tally) override;
+
+private:
+    std::shared_ptr<mocc::CorrectionData> corrections_;
+    std::shared_ptr<mocc::XSMeshHomogenized> sn_xs_mesh_;
+    mocc::ExpandedXS xstr_sn_;
+    bool internal_coupling_ = false;
+    std::vector<double> sn_col_, alpha_, beta_;
+    std::vector<std::vector<std::array<mocc::real_t, 3>>> correction_residuals_;
 };
 }

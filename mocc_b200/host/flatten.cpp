@@ -130,6 +130,30 @@ FlatProblem flatten(const mocc::CoreMesh &mesh, const mocc::moc::RayData &rays,
         }
     }
 
+    // ---- 2D3D correction-factor tables, same expressions as correction_worker.cpp:78-93 ----
+    for (int a = 0; a < n_ang; a++) {
+        fp.ang_area_x.push_back(std::abs(rays.spacing(a) / cos(aq[a].alpha)));
+        fp.ang_area_y.push_back(std::abs(rays.spacing(a) / sin(aq[a].alpha)));
+        fp.ang_ox.push_back(aq[a].ox);
+    }
+    for (int c = 0; c < fp.n_cell_plane; c++) {
+        auto pos = mesh.coarse_position(c);
+        fp.cell_dx.push_back(mesh.pin_dx()[pos.x]);
+        fp.cell_dy.push_back(mesh.pin_dy()[pos.y]);
+    }
+    {
+        // CurrentCorrections::mplane_offset_ (correction_worker.hpp:66-78)
+        int mplane = 0, offset = 0;
+        fp.plane_xs_offset.push_back(0);
+        for (const auto index : mesh.macroplane_index()) {
+            if (index != mplane) {
+                fp.plane_xs_offset.push_back(offset);
+                mplane = index;
+            }
+            offset += fp.n_cell_plane;
+        }
+    }
+
     // ---- boundary layout (BoundaryCondition ctor + update) ----
     fp.bc_size_x.assign(n_ang_bc, 0);
     fp.bc_size_y.assign(n_ang_bc, 0);
@@ -264,6 +288,8 @@ mocb200_problem FlatProblem::view() const
     p.plane_cell_offset = plane_cell_offset.data(), p.plane_surf_offset = plane_surf_offset.data();
     p.coarse_surf = coarse_surf.data(), p.coarse_nbr = coarse_nbr.data();
     p.vol = vol.data(), p.exp_table = exp_table.data();
+    p.ang_area_x = ang_area_x.data(), p.ang_area_y = ang_area_y.data(), p.ang_ox = ang_ox.data();
+    p.cell_dx = cell_dx.data(), p.cell_dy = cell_dy.data();
     return p;
 }
 
@@ -283,6 +309,7 @@ ArrayFile FlatProblem::to_arrayfile() const
     V_(seg_len), V_(seg_fsr), V_(cm_data);
     V_(plane_unique), V_(plane_first_reg), V_(plane_cell_offset), V_(plane_surf_offset);
     V_(plane_height), V_(plane_dz), V_(coarse_surf), V_(coarse_nbr), V_(vol), V_(surf_area), V_(exp_table);
+    V_(ang_area_x), V_(ang_area_y), V_(ang_ox), V_(cell_dx), V_(cell_dy), V_(plane_xs_offset);
 #undef S_
 #undef V_
     return af;
@@ -313,6 +340,7 @@ FlatProblem FlatProblem::from_arrayfile(const ArrayFile &af)
     V_(seg_len), V_(seg_fsr), V_(cm_data);
     V_(plane_unique), V_(plane_first_reg), V_(plane_cell_offset), V_(plane_surf_offset);
     V_(plane_height), V_(plane_dz), V_(coarse_surf), V_(coarse_nbr), V_(vol), V_(surf_area), V_(exp_table);
+    V_(ang_area_x), V_(ang_area_y), V_(ang_ox), V_(cell_dx), V_(cell_dy), V_(plane_xs_offset);
 #undef S_
 #undef V_
     return fp;

@@ -48,6 +48,9 @@ struct FlatProblem {
     std::vector<double> plane_height, plane_dz;
     std::vector<int32_t> coarse_surf, coarse_nbr;
     std::vector<double> vol, surf_area, exp_table;
+    // 2D3D correction-factor tables (cmdo::CurrentCorrections)
+    std::vector<double> ang_area_x, ang_area_y, ang_ox, cell_dx, cell_dy;
+    std::vector<int32_t> plane_xs_offset; // CurrentCorrections::mplane_offset_ (index into PIN-expanded XS)
     // reference segment count S: sum over macroplanes and ALL sweep angles (polar copies counted)
     int64_t n_seg_reference = 0;
     int64_t n_ray_reference = 0;

@@ -21,6 +21,11 @@
 
 #include "cuda_moc_sweeper.hpp"
 
+namespace mocc_b200 {
+// plane_sweeper_2d3d_cuda.cpp: the reference's PlaneSweeper_2D3D compiled around the CUDA MoC sweeper
+mocc::UP_Sweeper_t make_plane_sweeper_2d3d_cuda(const pugi::xml_node &input, const mocc::CoreMesh &mesh);
+}
+
 namespace mocc {
 namespace {
 using Maker = std::function<UP_Sweeper_t(const pugi::xml_node &, const CoreMesh &)>;
@@ -43,6 +48,18 @@ const std::map<std::string, std::pair<const char *, Maker>> &registry()
          {"Using a 2D3D sweeper",
           [](const pugi::xml_node &n, const CoreMesh &m) {
               return UP_Sweeper_t(new cmdo::PlaneSweeper_2D3D(n, m));
+          }}},
+        {"2d3d_cuda",
+         {"Using a 2D3D sweeper with the B200 (CUDA) MoC sweeper",
+          [](const pugi::xml_node &n, const CoreMesh &m) {
+              return mocc_b200::make_plane_sweeper_2d3d_cuda(n, m);
+          }}},
+        {"moc_2d3d_cuda",
+         {"Using a standalone 2D3D B200 (CUDA) MoC sweeper",
+          [](const pugi::xml_node &n, const CoreMesh &m) {
+              auto *swp = new mocc_b200::CudaMoCSweeper2D3D(n, m);
+              swp->set_self_coupling();
+              return UP_Sweeper_t(swp);
           }}},
         {"moc_2d3d",
          {"Using a standalone 2D3D MoC sweeper",

@@ -75,9 +75,44 @@ static int surface_to_normal(int s)
     return (s == 0 || s == 2) ? 0 : 1;
 }
 
-int moc_oracle_sweep1g(const mocb200_problem *p, int gs_boundary, int tally_mode, const double *xstr,
-                       const double *qbar, double *bc_in, double *flux_out, double *current,
-                       double *surface_flux, const double *surf_area)
+/* calculate_corrections, correction_worker.cpp:32-158, for one (macroplane, sweep angle) */
+static void calc_corrections(const mocb200_problem *p, int ip, int a, const double *surf_sum, const double *vol_sum,
+                             const double *sigt_sum, const double *sn_xs, double *alpha, double *beta)
+{
+    /* Surface enum: E=0, N=1, W=2, S=3 */
+    int surfs[2][4]; /* [FW/BW][XL, XR, YL, YR] */
+    const int n_cell_tot = p->n_plane * p->n_cell_plane;
+    surfs[0][2] = 3, surfs[0][3] = 1, surfs[1][2] = 1, surfs[1][3] = 3;
+    if (p->ang_ox[a] > 0.0) {
+        surfs[0][0] = 2, surfs[0][1] = 0, surfs[1][0] = 0, surfs[1][1] = 2;
+    } else {
+        surfs[0][0] = 0, surfs[0][1] = 2, surfs[1][0] = 2, surfs[1][1] = 0;
+    }
+    for (int ic = 0; ic < p->n_cell_plane; ic++) {
+        int icc       = ic + p->plane_cell_offset[ip];
+        double area_x = p->ang_area_x[a] / p->cell_dx[ic];
+        double area_y = p->ang_area_y[a] / p->cell_dy[ic];
+        double xstr   = sn_xs[ip * p->n_cell_plane + ic];
+        for (int d = 0; d < 2; d++) {
+            double psi_xl = surf_sum[p->coarse_surf[4 * ic + surfs[d][0]] * 2 + d] * area_x;
+            double psi_xr = surf_sum[p->coarse_surf[4 * ic + surfs[d][1]] * 2 + d] * area_x;
+            double psi_yl = surf_sum[p->coarse_surf[4 * ic + surfs[d][2]] * 2 + d] * area_y;
+            double psi_yr = surf_sum[p->coarse_surf[4 * ic + surfs[d][3]] * 2 + d] * area_y;
+            double ax     = vol_sum[ic * 2 + d] / (psi_xl + psi_xr);
+            double ay     = vol_sum[ic * 2 + d] / (psi_yl + psi_yr);
+            double b      = sigt_sum[ic * 2 + d] / xstr;
+            int iang      = a + d * p->n_ang;
+            alpha[((size_t)iang * n_cell_tot + icc) * 2 + 0] = ax;
+            alpha[((size_t)iang * n_cell_tot + icc) * 2 + 1] = ay;
+            beta[(size_t)iang * n_cell_tot + icc]            = b;
+        }
+    }
+}
+
+static int sweep1g_core(const mocb200_problem *p, int gs_boundary, int tally_mode, const double *xstr,
+                        const double *qbar, double *bc_in, double *flux_out, double *current,
+                        double *surface_flux, const double *surf_area, const double *xstr_true,
+                        const double *sn_xs, double *alpha, double *beta)
 {
     const int n_ang = p->n_ang;
     int64_t max_seg = 0;
@@ -92,6 +127,16 @@ int moc_oracle_sweep1g(const mocb200_problem *p, int gs_boundary, int tally_mode
     double *bc_out = (double *)calloc((size_t)p->bc_per_group, sizeof(double));
     if (!e_tau || !psi1 || !psi2 || !bc_out)
         return 1;
+    /* cmdo::CurrentCorrections per-angle buffers (correction_worker.hpp:49-54) */
+    double *surf_sum = NULL, *vol_sum = NULL, *vol_norm = NULL, *sigt_sum = NULL;
+    if (tally_mode == 2) {
+        surf_sum = (double *)malloc(sizeof(double) * 2 * (size_t)p->n_surf_plane);
+        vol_sum  = (double *)malloc(sizeof(double) * 2 * (size_t)p->n_cell_plane);
+        sigt_sum = (double *)malloc(sizeof(double) * 2 * (size_t)p->n_cell_plane);
+        vol_norm = (double *)malloc(sizeof(double) * (size_t)p->n_cell_plane);
+        if (!surf_sum || !vol_sum || !sigt_sum || !vol_norm)
+            return 1;
+    }
 
     for (int i = 0; i < p->n_reg; i++)
         flux_out[i] = 0.0;
@@ -112,6 +157,12 @@ int moc_oracle_sweep1g(const mocb200_problem *p, int gs_boundary, int tally_mode
             const double wt_v_st = p->wt_v_st[ip * n_ang + a];
             const double cw[2]   = {p->cur_wx[ip * n_ang + a], p->cur_wy[ip * n_ang + a]};
             const double fw[2]   = {p->flx_wx[ip * n_ang + a], p->flx_wy[ip * n_ang + a]};
+            if (tally_mode == 2) { /* set_angle zeroes the sums, correction_worker.hpp:207-221 */
+                memset(surf_sum, 0, sizeof(double) * 2 * (size_t)p->n_surf_plane);
+                memset(vol_sum, 0, sizeof(double) * 2 * (size_t)p->n_cell_plane);
+                memset(sigt_sum, 0, sizeof(double) * 2 * (size_t)p->n_cell_plane);
+                memset(vol_norm, 0, sizeof(double) * (size_t)p->n_cell_plane);
+            }
             const int geom       = p->ang_geom[a];
             const int64_t t0     = p->geom_trk_begin[(size_t)u * p->n_geom + geom];
             const int64_t t1     = p->geom_trk_begin[(size_t)u * p->n_geom + geom + 1];
@@ -189,7 +240,76 @@ int moc_oracle_sweep1g(const mocb200_problem *p, int gs_boundary, int tally_mode
                         }
                     }
                 }
+                if (tally_mode == 2) {
+                    /* cmdo::CurrentCorrections::post_ray, correction_worker.hpp:109-205: currents use the
+                     * plane offset, the per-angle sums are plane-local; the backward SURFACE FLUX is
+                     * subtracted here (:136-137, :194-195) where moc::Current adds it */
+                    int cell_fw = p->trk_cm_start[4 * t + 0], cell_bw = p->trk_cm_start[4 * t + 1];
+                    int surf_fw = p->trk_cm_start[4 * t + 2], surf_bw = p->trk_cm_start[4 * t + 3];
+                    int iseg_fw = 0, iseg_bw = nseg;
+                    int norm_fw = surf_normal_local(p, surf_fw), norm_bw = surf_normal_local(p, surf_bw);
+                    current[surf_fw + surf_off] += psi1[iseg_fw] * cw[norm_fw];
+                    current[surf_bw + surf_off] -= psi2[iseg_bw] * cw[norm_bw];
+                    surface_flux[surf_fw + surf_off] += psi1[iseg_fw] * fw[norm_fw];
+                    surface_flux[surf_bw + surf_off] -= psi2[iseg_bw] * fw[norm_bw];
+                    surf_sum[surf_fw * 2 + 0] += psi1[iseg_fw];
+                    surf_sum[surf_bw * 2 + 1] += psi2[iseg_bw];
+                    for (int64_t k = p->trk_cm_begin[t]; k < p->trk_cm_begin[t + 1]; k++) {
+                        uint32_t c = p->cm_data[k];
+                        int s_fw = c & 0xF, s_bw = (c >> 4) & 0xF;
+                        int n_fw = (c >> 8) & 0xFF, n_bw = (c >> 16) & 0xFF;
+                        if (s_fw != 7) {
+                            for (int i = 0; i < n_fw; i++) {
+                                int ireg       = fsr[iseg_fw] + first_reg;
+                                double tt      = rstheta * len[iseg_fw];
+                                double fluxvol = tt * qbar[ireg] + (psi1[iseg_fw] - psi1[iseg_fw + 1]) / xstr[ireg];
+                                vol_sum[cell_fw * 2 + 0] += fluxvol;
+                                vol_norm[cell_fw] += tt;
+                                sigt_sum[cell_fw * 2 + 0] += xstr_true[ireg] * fluxvol;
+                                iseg_fw++;
+                            }
+                            norm_fw = surface_to_normal(s_fw);
+                            surf_fw = p->coarse_surf[4 * cell_fw + s_fw];
+                            current[surf_fw + surf_off] += psi1[iseg_fw] * cw[norm_fw];
+                            surface_flux[surf_fw + surf_off] += psi1[iseg_fw] * fw[norm_fw];
+                            surf_sum[surf_fw * 2 + 0] += psi1[iseg_fw];
+                        }
+                        if (s_bw != 7) {
+                            for (int i = 0; i < n_bw; i++) {
+                                iseg_bw--;
+                                int ireg       = fsr[iseg_bw] + first_reg;
+                                double tt      = rstheta * len[iseg_bw];
+                                double fluxvol = tt * qbar[ireg] +
+                                                 e_tau[iseg_bw] * (psi2[iseg_bw + 1] - qbar[ireg]) / xstr[ireg];
+                                vol_sum[cell_bw * 2 + 1] += fluxvol;
+                                sigt_sum[cell_bw * 2 + 1] += xstr_true[ireg] * fluxvol;
+                            }
+                            norm_bw = surface_to_normal(s_bw);
+                            surf_bw = p->coarse_surf[4 * cell_bw + s_bw];
+                            current[surf_bw + surf_off] -= psi2[iseg_bw] * cw[norm_bw];
+                            surface_flux[surf_bw + surf_off] -= psi2[iseg_bw] * fw[norm_bw];
+                            surf_sum[surf_bw * 2 + 1] += psi2[iseg_bw];
+                        }
+                        if (s_fw < 4) {
+                            int nb  = p->coarse_nbr[4 * cell_fw + s_fw];
+                            cell_fw = (nb < 0) ? cell_fw : nb;
+                        }
+                        if (s_bw < 4) {
+                            int nb  = p->coarse_nbr[4 * cell_bw + s_bw];
+                            cell_bw = (nb < 0) ? cell_bw : nb;
+                        }
+                    }
+                }
             } /* rays */
+            if (tally_mode == 2) { /* post_angle, correction_worker.hpp:223-246 */
+                for (int i = 0; i < p->n_cell_plane; i++) {
+                    sigt_sum[2 * i + 0] /= vol_sum[2 * i + 0];
+                    sigt_sum[2 * i + 1] /= vol_sum[2 * i + 1];
+                    vol_sum[2 * i + 0] /= vol_norm[i];
+                    vol_sum[2 * i + 1] /= vol_norm[i];
+                }
+                calc_corrections(p, ip, a, surf_sum, vol_sum, sigt_sum, sn_xs, alpha, beta);
+            }
             if (gs_boundary) {
                 bc_update_angle(p, a1, b_in, bc_out);
                 bc_update_angle(p, a2, b_in, bc_out);
@@ -205,7 +325,13 @@ int moc_oracle_sweep1g(const mocb200_problem *p, int gs_boundary, int tally_mode
     for (int i = 0; i < p->n_reg; i++)
         flux_out[i] = flux_out[i] / (xstr[i] * p->vol[i]) + qbar[i] * FPI_;
 
-    if (tally_mode == 1) {
+    if (tally_mode == 2) {
+        free(surf_sum);
+        free(vol_sum);
+        free(sigt_sum);
+        free(vol_norm);
+    }
+    if (tally_mode >= 1) {
         /* post_sweep normalisation, moc_current_worker.hpp:303-316 (no sub-plane expansion here:
          * callers with sub-planes expand on the host exactly like the reference) */
         for (int ip = 0; ip < p->n_plane; ip++) {
@@ -222,4 +348,25 @@ int moc_oracle_sweep1g(const mocb200_problem *p, int gs_boundary, int tally_mode
     free(psi2);
     free(bc_out);
     return 0;
+}
+
+int moc_oracle_sweep1g(const mocb200_problem *p, int gs_boundary, int tally_mode, const double *xstr,
+                       const double *qbar, double *bc_in, double *flux_out, double *current,
+                       double *surface_flux, const double *surf_area)
+{
+    if (tally_mode != 0 && tally_mode != 1)
+        return 2;
+    return sweep1g_core(p, gs_boundary, tally_mode, xstr, qbar, bc_in, flux_out, current, surface_flux, surf_area,
+                        NULL, NULL, NULL, NULL);
+}
+
+int moc_oracle_sweep1g_corrections(const mocb200_problem *p, int gs_boundary, const double *xstr_split,
+                                   const double *xstr_true, const double *qbar, const double *sn_xs, double *bc_in,
+                                   double *flux_out, double *current, double *surface_flux, const double *surf_area,
+                                   double *alpha, double *beta)
+{
+    if (!p->ang_area_x || !p->ang_area_y || !p->ang_ox || !p->cell_dx || !p->cell_dy)
+        return 2;
+    return sweep1g_core(p, gs_boundary, 2, xstr_split, qbar, bc_in, flux_out, current, surface_flux, surf_area,
+                        xstr_true, sn_xs, alpha, beta);
 }

@@ -36,6 +36,11 @@
 #include "solvers/solver_factory.hpp"
 #include "sweepers/moc/moc_current_worker.hpp"
 #include "sweepers/moc/moc_sweeper.hpp"
+// the 2D3D MoC sweeper keeps its coupling objects private; the tool records them
+#define private protected
+#include "sweepers/cmdo/moc_sweeper_2d3d.hpp"
+#undef private
+#include "sweepers/cmdo/correction_worker.hpp"
 #include "util/files.hpp"
 
 #include "arrayfile.hpp"
@@ -54,43 +59,44 @@ struct RecordKey {
     }
 };
 
-// Gives the tool access to MoCSweeper's protected state and to the reference
-// kernel sweep1g<>. sweep_recorded() follows MoCSweeper::sweep
-// (moc_sweeper.cpp:189-225) step by step so that inputs and outputs of every
-// sweep1g call can be captured.
-class ExposedMoC : public moc::MoCSweeper {
+// Gives the tool access to the sweeper's protected state and to the reference kernel
+// sweep1g<>. sweep_recorded() follows MoCSweeper::sweep (moc_sweeper.cpp:189-225) step by
+// step so that inputs and outputs of every sweep1g call can be captured;
+// Exposed2D3D::sweep_recorded() does the same for MoCSweeper_2D3D::sweep
+// (cmdo/moc_sweeper_2d3d.cpp:48-99) with the reference's CurrentCorrections worker.
+template <class Base> class ExposedT : public Base {
 public:
-    ExposedMoC(const pugi::xml_node &input, const CoreMesh &mesh) : moc::MoCSweeper(input, mesh)
+    ExposedT(const pugi::xml_node &input, const CoreMesh &mesh) : Base(input, mesh)
     {
     }
 
     mocc_b200::FlatProblem flat() const
     {
-        std::vector<double> vol(vol_.begin(), vol_.end());
-        return mocc_b200::flatten(mesh_, rays_, macroplane_unique_ids_, first_reg_macroplane_,
-                                  vol.data(), (int)n_reg_, (int)n_group_);
+        std::vector<double> vol(this->vol_.begin(), this->vol_.end());
+        return mocc_b200::flatten(this->mesh_, this->rays_, this->macroplane_unique_ids_,
+                                  this->first_reg_macroplane_, vol.data(), (int)this->n_reg_, (int)this->n_group_);
     }
     Source *source()
     {
-        return source_;
+        return this->source_;
     }
     int n_inner() const
     {
-        return n_inner_;
+        return this->n_inner_;
     }
     bool gs() const
     {
-        return gauss_seidel_boundary_;
+        return this->gauss_seidel_boundary_;
     }
     int bc_per_group() const
     {
-        return boundary_[0].size() / n_group_;
+        return this->boundary_[0].size() / this->n_group_;
     }
     std::vector<double> bc_in(int group) const
     {
         std::vector<double> out;
         int n = bc_per_group();
-        for (const auto &b : boundary_) {
+        for (const auto &b : this->boundary_) {
             const real_t *p = b.get_boundary(group, 0).second;
             out.insert(out.end(), p, p + n);
         }
@@ -98,8 +104,8 @@ public:
     }
     std::vector<double> xs_per_reg(int group, int which) const
     {
-        std::vector<double> out(n_reg_);
-        for (const auto &xsr : *xs_mesh_) {
+        std::vector<double> out(this->n_reg_);
+        for (const auto &xsr : *this->xs_mesh_) {
             double v = 0.0;
             switch (which) {
             case 0:
@@ -123,69 +129,193 @@ public:
     // scattering matrix expanded to FSRs: out[gfrom][ireg] for scattering INTO `group`
     std::vector<double> xs_scat_to(int group) const
     {
-        std::vector<double> out((size_t)n_group_ * n_reg_, 0.0);
-        for (const auto &xsr : *xs_mesh_) {
+        std::vector<double> out((size_t)this->n_group_ * this->n_reg_, 0.0);
+        for (const auto &xsr : *this->xs_mesh_) {
             const ScatteringRow &row = xsr.xsmacsc().to(group);
             for (int gf = row.min_g; gf <= row.max_g; gf++)
                 for (const int ireg : xsr.reg())
-                    out[(size_t)gf * n_reg_ + ireg] = row[gf];
+                    out[(size_t)gf * this->n_reg_ + ireg] = row[gf];
         }
         return out;
     }
 
-    void sweep_recorded(int group, int outer, const std::set<RecordKey> &want, ArrayFile &out, int &n_rec)
+    void record_inputs(ArrayFile &out, const std::string &p, int outer, int group, int inner)
+    {
+        out.put_scalar<int32_t>(p + "outer", outer);
+        out.put_scalar<int32_t>(p + "group", group);
+        out.put_scalar<int32_t>(p + "inner", inner);
+        std::vector<double> fin(this->flux_1g_.begin(), this->flux_1g_.end());
+        out.put(p + "flux_in", fin);
+        const VectorX &s = this->source_->get();
+        out.put(p + "src", s.data(), {(uint64_t)s.size()});
+        out.put(p + "bc_in", bc_in(group));
+    }
+    void record_source(ArrayFile &out, const std::string &p)
+    {
+        const VectorX &q = this->source_->get_transport(0);
+        out.put(p + "qbar", q.data(), {(uint64_t)q.size()});
+        std::vector<double> x(this->xstr_.xs().begin(), this->xstr_.xs().end());
+        out.put(p + "xstr", x);
+    }
+    void record_outputs(ArrayFile &out, const std::string &p, int group, int mode)
+    {
+        out.put_scalar<int32_t>(p + "mode", mode);
+        std::vector<double> fout(this->flux_1g_.begin(), this->flux_1g_.end());
+        out.put(p + "flux_out", fout);
+        out.put(p + "bc_out", bc_in(group));
+        if (mode != 0) {
+            auto all = blitz::Range::all();
+            auto c   = this->coarse_data_->current(all, group);
+            auto sf  = this->coarse_data_->surface_flux(all, group);
+            std::vector<double> cv(c.begin(), c.end()), sv(sf.begin(), sf.end());
+            out.put(p + "current", cv);
+            out.put(p + "surface_flux", sv);
+        }
+    }
+
+    virtual void sweep_recorded(int group, int outer, const std::set<RecordKey> &want, ArrayFile &out, int &n_rec)
+    {
+        this->xstr_.expand(group, this->split_);
+        this->flux_1g_.reference(this->flux_(blitz::Range::all(), group));
+        for (unsigned int inner = 0; inner < this->n_inner_; inner++) {
+            bool rec = want.count(RecordKey{outer, group, (int)inner}) != 0;
+            std::string p = "rec" + std::to_string(n_rec) + "_";
+            if (rec)
+                record_inputs(out, p, outer, group, (int)inner);
+            this->source_->self_scatter(group, this->xstr_.xs());
+            if (rec)
+                record_source(out, p);
+            int mode = 0;
+            if (inner == this->n_inner_ - 1 && this->coarse_data_) {
+                this->coarse_data_->zero_data_radial(group);
+                moc::Current cw(this->coarse_data_, &this->mesh_);
+                this->sweep1g(group, cw);
+                this->coarse_data_->set_has_radial_data(true);
+                mode = 1;
+            } else {
+                moc::NoCurrent cw(this->coarse_data_, &this->mesh_);
+                this->sweep1g(group, cw);
+            }
+            if (rec) {
+                record_outputs(out, p, group, mode);
+                n_rec++;
+            }
+        }
+    }
+};
+using ExposedMoC = ExposedT<moc::MoCSweeper>;
+
+class Exposed2D3D : public ExposedT<cmdo::MoCSweeper_2D3D> {
+public:
+    Exposed2D3D(const pugi::xml_node &input, const CoreMesh &mesh) : ExposedT<cmdo::MoCSweeper_2D3D>(input, mesh)
+    {
+        set_self_coupling();
+    }
+    void sweep_recorded(int group, int outer, const std::set<RecordKey> &want, ArrayFile &out, int &n_rec) override
     {
         xstr_.expand(group, split_);
+        if (allow_splitting_)
+            xstr_true_.expand(group);
+        cmdo::CurrentCorrections ccw(coarse_data_, &mesh_, corrections_.get(), source_->get_transport(0), xstr_true_,
+                                     xstr_, xstr_sn_, ang_quad_, rays_);
+        moc::NoCurrent ncw(coarse_data_, &mesh_);
         flux_1g_.reference(flux_(blitz::Range::all(), group));
         for (unsigned int inner = 0; inner < n_inner_; inner++) {
             bool rec = want.count(RecordKey{outer, group, (int)inner}) != 0;
             std::string p = "rec" + std::to_string(n_rec) + "_";
-            if (rec) {
-                out.put_scalar<int32_t>(p + "outer", outer);
-                out.put_scalar<int32_t>(p + "group", group);
-                out.put_scalar<int32_t>(p + "inner", (int)inner);
-                std::vector<double> fin(flux_1g_.begin(), flux_1g_.end());
-                out.put(p + "flux_in", fin);
-                const VectorX &s = source_->get();
-                out.put(p + "src", s.data(), {(uint64_t)s.size()});
-                out.put(p + "bc_in", bc_in(group));
-            }
+            if (rec)
+                record_inputs(out, p, outer, group, (int)inner);
             source_->self_scatter(group, xstr_.xs());
-            if (rec) {
-                const VectorX &q = source_->get_transport(0);
-                out.put(p + "qbar", q.data(), {(uint64_t)q.size()});
-                std::vector<double> x(xstr_.xs().begin(), xstr_.xs().end());
-                out.put(p + "xstr", x);
-            }
+            if (rec)
+                record_source(out, p);
             int mode = 0;
             if (inner == n_inner_ - 1 && coarse_data_) {
                 coarse_data_->zero_data_radial(group);
-                moc::Current cw(coarse_data_, &mesh_);
-                this->sweep1g(group, cw);
+                sn_xs_mesh_->update();
+                this->sweep1g(group, ccw);
                 coarse_data_->set_has_radial_data(true);
-                mode = 1;
+                mode = 2;
             } else {
-                moc::NoCurrent cw(coarse_data_, &mesh_);
-                this->sweep1g(group, cw);
+                this->sweep1g(group, ncw);
             }
             if (rec) {
-                out.put_scalar<int32_t>(p + "mode", mode);
-                std::vector<double> fout(flux_1g_.begin(), flux_1g_.end());
-                out.put(p + "flux_out", fout);
-                out.put(p + "bc_out", bc_in(group));
-                if (mode == 1) {
-                    auto all = blitz::Range::all();
-                    auto c   = coarse_data_->current(all, group);
-                    auto sf  = coarse_data_->surface_flux(all, group);
-                    std::vector<double> cv(c.begin(), c.end()), sv(sf.begin(), sf.end());
-                    out.put(p + "current", cv);
-                    out.put(p + "surface_flux", sv);
+                record_outputs(out, p, group, mode);
+                if (mode == 2) {
+                    std::vector<double> xt(xstr_true_.xs().begin(), xstr_true_.xs().end());
+                    out.put(p + "xstr_true", xt);
+                    // homogenised XS the beta factor divides by (correction_worker.cpp:84-93)
+                    auto fp = this->flat();
+                    xstr_sn_.expand(group);
+                    std::vector<double> sn;
+                    for (int ip = 0; ip < fp.n_plane; ip++)
+                        for (int ic = 0; ic < fp.n_cell_plane; ic++)
+                            sn.push_back(xstr_sn_[ic + fp.plane_xs_offset[ip]]);
+                    out.put(p + "sn_xs", sn);
+                    const int n_ang2 = ang_quad_.ndir() / 2, n_cell = corrections_->n_cell();
+                    std::vector<double> al((size_t)n_ang2 * n_cell * 2), be((size_t)n_ang2 * n_cell);
+                    for (int ia = 0; ia < n_ang2; ia++)
+                        for (int ic = 0; ic < n_cell; ic++) {
+                            al[((size_t)ia * n_cell + ic) * 2 + 0] = corrections_->alpha(ic, ia, group, Normal::X_NORM);
+                            al[((size_t)ia * n_cell + ic) * 2 + 1] = corrections_->alpha(ic, ia, group, Normal::Y_NORM);
+                            be[(size_t)ia * n_cell + ic]           = corrections_->beta(ic, ia, group);
+                        }
+                    out.put(p + "alpha", al);
+                    out.put(p + "beta", be);
                 }
                 n_rec++;
             }
         }
     }
 };
+
+
+std::set<RecordKey> parse_records(const std::string &s);
+
+template <class SW> int run_golden(SW &sw, Source &source_ref, const std::string &out_path, int outers,
+                                   const std::string &records)
+{
+    Source *source = &source_ref;
+    const int ng   = sw.n_group();
+    auto fp        = sw.flat();
+    fp.to_arrayfile().save(out_path + ".mocflat");
+    ArrayFile out;
+    out.put_scalar<int32_t>("n_inner", sw.n_inner());
+    out.put_scalar<int32_t>("gs_boundary", sw.gs() ? 1 : 0);
+    out.put_scalar<int32_t>("n_outer", outers);
+    for (int g = 0; g < ng; g++) {
+        out.put("xs_tr_" + std::to_string(g), sw.xs_per_reg(g, 0));
+        out.put("xs_self_" + std::to_string(g), sw.xs_per_reg(g, 1));
+        out.put("xs_nf_" + std::to_string(g), sw.xs_per_reg(g, 2));
+        out.put("xs_ch_" + std::to_string(g), sw.xs_per_reg(g, 3));
+        out.put("xs_scat_to_" + std::to_string(g), sw.xs_scat_to(g));
+    }
+    std::set<RecordKey> want = parse_records(records);
+    sw.initialize();
+    real_t k = 1.0;
+    ArrayB1 fs(sw.n_reg());
+    int n_rec = 0;
+    std::vector<double> khist;
+    for (int outer = 0; outer < outers; outer++) {
+        sw.calc_fission_source(k, fs);
+        sw.store_old_flux();
+        for (int ig = 0; ig < ng; ig++) {
+            source->initialize_group(ig);
+            source->fission(fs, ig);
+            source->in_scatter(ig);
+            sw.sweep_recorded(ig, outer, want, out, n_rec);
+        }
+        k = k * sw.total_fission(false) / sw.total_fission(true);
+        khist.push_back(k);
+    }
+    out.put_scalar<int32_t>("n_rec", n_rec);
+    out.put("k_history", khist);
+    const ArrayB2 &flux = sw.flux();
+    std::vector<double> f(flux.begin(), flux.end());
+    out.put("flux_final", f.data(), {(uint64_t)flux.extent(0), (uint64_t)flux.extent(1)});
+    out.save(out_path + ".golden");
+    std::printf("golden: %d records, k after %d outers = %.12f\n", n_rec, outers, (double)k);
+    return 0;
+}
 
 void set_xml(pugi::xml_document &doc, const std::string &spec)
 {
@@ -241,7 +371,7 @@ int main(int argc, char **argv)
         std::string out_path;
         std::vector<std::string> sets;
         int outers = 1, sweeps = 2, warmup = 1;
-        bool cmfd  = false;
+        bool cmfd = false, twod3d = false;
         std::string records;
         for (int i = 3; i < argc; i++) {
             std::string a = argv[i];
@@ -257,6 +387,8 @@ int main(int argc, char **argv)
                 records = argv[++i];
             else if (a == "--cmfd")
                 cmfd = true;
+            else if (a == "--2d3d")
+                twod3d = cmfd = true;
             else if (out_path.empty())
                 out_path = a;
             else
@@ -300,7 +432,23 @@ int main(int argc, char **argv)
 
         CoreMesh mesh(doc);
         pugi::xml_node solver_node = doc.child("solver");
-        ExposedMoC sw(solver_node.child("sweeper"), mesh);
+        std::unique_ptr<ExposedMoC> sw_moc;
+        std::unique_ptr<Exposed2D3D> sw_2d3d;
+        if (twod3d)
+            sw_2d3d.reset(new Exposed2D3D(solver_node.child("sweeper"), mesh));
+        else
+            sw_moc.reset(new ExposedMoC(solver_node.child("sweeper"), mesh));
+        if (twod3d && cmd != "golden")
+            throw std::runtime_error("--2d3d only applies to the golden command");
+        if (twod3d) {
+            Exposed2D3D &sw = *sw_2d3d;
+            UP_Source_t source = sw.create_source(solver_node.child("source"));
+            sw.assign_source(source.get());
+            std::unique_ptr<CoarseData> cd(new CoarseData(mesh, sw.n_group()));
+            sw.set_coarse_data(cd.get());
+            return run_golden(sw, *source, out_path, outers, records);
+        }
+        ExposedMoC &sw = *sw_moc;
 
         if (cmd == "flat") {
             sw.flat().to_arrayfile().save(out_path);
@@ -316,47 +464,8 @@ int main(int argc, char **argv)
         }
         const int ng = sw.n_group();
 
-        if (cmd == "golden") {
-            auto fp = sw.flat();
-            fp.to_arrayfile().save(out_path + ".mocflat");
-            ArrayFile out;
-            out.put_scalar<int32_t>("n_inner", sw.n_inner());
-            out.put_scalar<int32_t>("gs_boundary", sw.gs() ? 1 : 0);
-            out.put_scalar<int32_t>("n_outer", outers);
-            for (int g = 0; g < ng; g++) {
-                out.put("xs_tr_" + std::to_string(g), sw.xs_per_reg(g, 0));
-                out.put("xs_self_" + std::to_string(g), sw.xs_per_reg(g, 1));
-                out.put("xs_nf_" + std::to_string(g), sw.xs_per_reg(g, 2));
-                out.put("xs_ch_" + std::to_string(g), sw.xs_per_reg(g, 3));
-                out.put("xs_scat_to_" + std::to_string(g), sw.xs_scat_to(g));
-            }
-            std::set<RecordKey> want = parse_records(records);
-            sw.initialize();
-            real_t k = 1.0;
-            ArrayB1 fs(sw.n_reg());
-            int n_rec = 0;
-            std::vector<double> khist;
-            for (int outer = 0; outer < outers; outer++) {
-                sw.calc_fission_source(k, fs);
-                sw.store_old_flux();
-                for (int ig = 0; ig < ng; ig++) {
-                    source->initialize_group(ig);
-                    source->fission(fs, ig);
-                    source->in_scatter(ig);
-                    sw.sweep_recorded(ig, outer, want, out, n_rec);
-                }
-                k = k * total_fission(sw, false) / total_fission(sw, true);
-                khist.push_back(k);
-            }
-            out.put_scalar<int32_t>("n_rec", n_rec);
-            out.put("k_history", khist);
-            const ArrayB2 &flux = sw.flux();
-            std::vector<double> f(flux.begin(), flux.end());
-            out.put("flux_final", f.data(), {(uint64_t)flux.extent(0), (uint64_t)flux.extent(1)});
-            out.save(out_path + ".golden");
-            std::printf("golden: %d records, k after %d outers = %.12f\n", n_rec, outers, (double)k);
-            return 0;
-        }
+        if (cmd == "golden")
+            return run_golden(sw, *source, out_path, outers, records);
 
         if (cmd == "time") {
             // Time `sweeps` full passes (every group once, n_inner inners each) of the

@@ -36,6 +36,7 @@ CASES = {
     "mini2d_nocmfd": ("mini2d_gs.mocflat.gz", "mini2d_nocmfd.golden.gz"),
     "mini3d_gs": ("mini3d_gs.mocflat.gz", "mini3d_gs.golden.gz"),
     "3x3_s05_gs": ("3x3_s05_gs.mocflat.gz", "3x3_s05_gs.golden.gz"),
+    "mini3d_2d3d": ("mini3d_gs.mocflat.gz", "mini3d_2d3d.golden.gz"),
 }
 
 _cache = {}

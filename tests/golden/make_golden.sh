@@ -21,7 +21,7 @@ run() { # name xml records [extra args...]
         || { tail -20 "$WORK/$name.log"; exit 1; }
     tail -1 "$WORK/$name.log"
     # geometry shared with mini2d_gs is stored once
-    case "$name" in mini2d_jacobi|mini2d_nocmfd) ;; *) gzip -9 -n -c "$WORK/$name.mocflat" > "$HERE/$name.mocflat.gz";; esac
+    case "$name" in mini2d_jacobi|mini2d_nocmfd|mini3d_2d3d) ;; *) gzip -9 -n -c "$WORK/$name.mocflat" > "$HERE/$name.mocflat.gz";; esac
     gzip -9 -n -c "$WORK/$name.golden" > "$HERE/$name.golden.gz"
 }
 
@@ -29,5 +29,23 @@ run mini2d_gs     mini2d.xml "0:0:0,0:1:2,1:2:2,1:0:1" --cmfd
 run mini2d_jacobi mini2d.xml "0:0:0,0:1:2,1:2:2" --cmfd --set solver/sweeper@boundary_update=jacobi
 run mini2d_nocmfd mini2d.xml "0:0:2,1:1:2"
 run mini3d_gs     mini3d.xml "0:0:0,0:1:1,1:2:1" --cmfd
+# MoCSweeper_2D3D + cmdo::CurrentCorrections (self-coupled): last inner records alpha/beta
+run mini3d_2d3d   mini3d.xml "0:0:1,0:2:1,1:1:1" --2d3d
 run 3x3_s05_gs    3x3.xml    "0:0:0,0:3:4,1:6:4" --cmfd --set solver/sweeper/rays@spacing=0.05
 ls -la "$HERE"/*.gz
+
+# whole-solve goldens: the reference solver stack with the reference CPU sweepers
+# (mocc_b200/bin/mocc_b200_solve = unmodified EigenSolver/CMFD/2D3D; <sweeper type> as in the input)
+SOLVE="$ROOT/mocc_b200/bin/mocc_b200_solve"
+python_pack() { python - "$1" "$2" <<'PY'
+import sys
+sys.path.insert(0, sys.argv[0] and ".")
+from mocc_b200 import load_arrays, save_arrays
+save_arrays(sys.argv[2], load_arrays(sys.argv[1]))
+PY
+}
+for c in mini2d mini2d3d 3x3; do
+    "$SOLVE" "$c.xml" "$WORK/$c.arrays" > "$WORK/$c.solve.log" 2>&1 || { tail -5 "$WORK/$c.solve.log"; exit 1; }
+    tail -1 "$WORK/$c.solve.log"
+    (cd "$ROOT" && python_pack "$WORK/$c.arrays" "$HERE/${c}_solve_ref.arrays.gz")
+done

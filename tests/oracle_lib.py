@@ -28,6 +28,7 @@ def oracle():
         lib.moc_oracle_self_scatter.restype = None
         lib.moc_oracle_sweep1g.argtypes = [C.POINTER(Problem), C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p,
                                            _f64p, _f64p, _f64p]
+        lib.moc_oracle_sweep1g_corrections.argtypes = [C.POINTER(Problem), C.c_int] + [_f64p] * 11
         _lib = lib
     return _lib
 
@@ -63,3 +64,20 @@ def oracle_sweep1g(arrays, xstr, qbar, bc_in, gs_boundary=True, tally_mode=0):
     if rc != 0:
         raise RuntimeError("oracle sweep failed")
     return flux, bc, cur, sf
+
+
+def oracle_sweep1g_corrections(arrays, xstr_split, xstr_true, qbar, sn_xs, bc_in, gs_boundary=True):
+    """sweep1g<cmdo::CurrentCorrections>: returns (flux, bc_after, current, surface_flux, alpha, beta)."""
+    prob, keep = problem_from_arrays(arrays)
+    xs, xt, q, sn = (np.ascontiguousarray(x, dtype=np.float64) for x in (xstr_split, xstr_true, qbar, sn_xs))
+    bc = np.array(bc_in, dtype=np.float64, copy=True).reshape(prob.n_plane, prob.bc_per_group)
+    n_cell = prob.n_plane * prob.n_cell_plane
+    flux, cur, sf = np.zeros(prob.n_reg), np.zeros(prob.n_surf), np.zeros(prob.n_surf)
+    alpha = np.full((2 * prob.n_ang, n_cell, 2), np.nan)
+    beta = np.full((2 * prob.n_ang, n_cell), np.nan)
+    area = np.ascontiguousarray(arrays["surf_area"], dtype=np.float64)
+    rc = oracle().moc_oracle_sweep1g_corrections(C.byref(prob), int(gs_boundary), _p(xs), _p(xt), _p(q), _p(sn),
+                                                 _p(bc), _p(flux), _p(cur), _p(sf), _p(area), _p(alpha), _p(beta))
+    if rc != 0:
+        raise RuntimeError(f"oracle corrections sweep failed ({rc})")
+    return flux, bc, cur, sf, alpha, beta
