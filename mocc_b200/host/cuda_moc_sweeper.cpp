@@ -27,7 +27,16 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
     mocb200_options opt{};
     opt.boundary_update = gauss_seidel_boundary_ ? MOCB200_BOUNDARY_GS : MOCB200_BOUNDARY_JACOBI;
     const pugi::xml_node cu = input.child("cuda");
-    opt.device              = cu.attribute("device").as_int(0);
+    std::vector<int> devices;
+    {
+        std::stringstream ds(cu.attribute("devices").as_string(""));
+        std::string tok;
+        while (std::getline(ds, tok, ','))
+            if (!tok.empty())
+                devices.push_back(std::stoi(tok));
+        if (devices.empty())
+            devices.push_back(cu.attribute("device").as_int(0));
+    }
     opt.max_polar           = cu.attribute("max_polar").as_int(0);
     group_batch_            = cu.attribute("group_batch").as_bool(false);
     std::string kernel      = cu.attribute("kernel").as_string("auto");
@@ -54,16 +63,53 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
     if (n_bc_ * (int)n_group_ != boundary_[0].size())
         throw EXCEPT("Flattened boundary layout does not match BoundaryCondition storage.");
     mocb200_problem prob = fp.view();
-    int rc               = mocb200_create(&prob, &opt, &dev_);
-    if (rc != MOCB200_OK) {
-        std::stringstream msg;
-        msg << "mocb200_create failed (" << rc << "): " << mocb200_last_error(nullptr);
-        throw EXCEPT(msg.str());
+    // contiguous macroplane ranges, balanced by the segments each plane's ray set holds
+    std::vector<double> plane_w(n_macroplane_, 0.0);
+    for (int ip = 0; ip < n_macroplane_; ip++) {
+        const int u = macroplane_unique_ids_[ip];
+        for (int gi = 0; gi < fp.n_geom; gi++) {
+            const int64_t t0 = fp.geom_trk_begin[(size_t)u * fp.n_geom + gi], t1 = fp.geom_trk_begin[(size_t)u * fp.n_geom + gi + 1];
+            plane_w[ip] += (double)(fp.trk_seg_begin[t1] - fp.trk_seg_begin[t0]);
+        }
     }
-    mocb200_get_stats(dev_, &stats_);
-    LogFile << "B200 MoC sweeper: " << fp.n_seg_reference << " segments (" << stats_.unique_segments
-            << " resident after polar sharing), " << stats_.device_bytes / (1024.0 * 1024.0) << " MiB on device"
-            << std::endl;
+    const int n_part = std::min<int>((int)devices.size(), n_macroplane_);
+    double w_total = 0.0;
+    for (double w : plane_w)
+        w_total += w;
+    int ip = 0;
+    double w_done = 0.0;
+    for (int k = 0; k < n_part; k++) {
+        Part part;
+        part.device      = devices[k];
+        part.plane_begin = ip;
+        const double target = w_total * (k + 1) / n_part;
+        while (ip < n_macroplane_ && (ip == part.plane_begin || w_done + 0.5 * plane_w[ip] < target) &&
+               n_macroplane_ - ip > n_part - 1 - k) {
+            w_done += plane_w[ip];
+            ip++;
+        }
+        if (k == n_part - 1)
+            ip = n_macroplane_;
+        part.plane_end = ip;
+        part.reg_lo    = first_reg_macroplane_[part.plane_begin];
+        part.reg_hi    = part.plane_end < n_macroplane_ ? first_reg_macroplane_[part.plane_end] : (int)n_reg_;
+        opt.device      = part.device;
+        opt.plane_begin = part.plane_begin;
+        opt.plane_end   = part.plane_end;
+        int rc          = mocb200_create(&prob, &opt, &part.h);
+        if (rc != MOCB200_OK) {
+            std::stringstream msg;
+            msg << "mocb200_create failed (" << rc << "): " << mocb200_last_error(nullptr);
+            throw EXCEPT(msg.str());
+        }
+        parts_.push_back(part);
+        mocb200_get_stats(part.h, &stats_);
+        LogFile << "B200 MoC sweeper: device " << part.device << " owns macroplanes [" << part.plane_begin << ", "
+                << part.plane_end << "): " << stats_.segments_per_sweep << " segments per sweep, "
+                << stats_.device_bytes / (1024.0 * 1024.0) << " MiB on device" << std::endl;
+    }
+    LogFile << "B200 MoC sweeper: " << fp.n_seg_reference << " segments (" << fp.seg_len.size()
+            << " resident after polar sharing) on " << parts_.size() << " GPU(s)" << std::endl;
 
     // ---- per-FSR cross sections the device-side self-scatter source needs ----
     xstr_true_fsr_.assign((size_t)n_group_ * n_reg_, 0.0);
@@ -89,22 +135,23 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
 
 CudaMoCSweeper::~CudaMoCSweeper()
 {
-    if (dev_)
-        mocb200_destroy(dev_);
+    for (auto &p : parts_)
+        if (p.h)
+            mocb200_destroy(p.h);
 }
 
-void CudaMoCSweeper::check(int rc, const char *what) const
+void CudaMoCSweeper::check(const Part &p, int rc, const char *what) const
 {
     if (rc != MOCB200_OK) {
         std::stringstream msg;
-        msg << what << " failed (" << rc << "): " << mocb200_last_error(dev_);
+        msg << what << " failed on device " << p.device << " (" << rc << "): " << mocb200_last_error(p.h);
         throw EXCEPT(msg.str());
     }
 }
 
 const mocb200_stats &CudaMoCSweeper::device_stats()
 {
-    mocb200_get_stats(dev_, &stats_);
+    mocb200_get_stats(parts_[0].h, &stats_);
     return stats_;
 }
 
@@ -114,47 +161,57 @@ void CudaMoCSweeper::upload_group(int group)
 {
     // ExpandedXS::expand as MoCSweeper::sweep does it (moc_sweeper.cpp:197)
     xstr_.expand(group, split_);
-    if (!xs_uploaded_[group] || allow_splitting_) {
+    const bool send_xs = !xs_uploaded_[group] || allow_splitting_;
+    if (send_xs)
         std::copy(xstr_.xs().begin(), xstr_.xs().end(), col_.begin());
-        check(mocb200_set_xs(dev_, group, 1, col_.data(), &xstr_true_fsr_[(size_t)group * n_reg_],
-                             &xs_self_fsr_[(size_t)group * n_reg_]),
-              "mocb200_set_xs");
-        xs_uploaded_[group] = true;
-    }
     const VectorX &src = source_->get();
-    check(mocb200_set_source(dev_, group, 1, src.data()), "mocb200_set_source");
+    for (const Part &p : parts_) {
+        if (send_xs)
+            check(p, mocb200_set_xs(p.h, group, 1, col_.data(), &xstr_true_fsr_[(size_t)group * n_reg_],
+                                    &xs_self_fsr_[(size_t)group * n_reg_]),
+                  "mocb200_set_xs");
+        check(p, mocb200_set_source(p.h, group, 1, src.data()), "mocb200_set_source");
+    }
+    xs_uploaded_[group] = true;
     for (int ireg = 0; ireg < (int)n_reg_; ireg++)
         col_[ireg] = flux_(ireg, group);
-    check(mocb200_set_flux(dev_, group, 1, col_.data()), "mocb200_set_flux");
-    for (int ip = 0; ip < n_macroplane_; ip++)
-        check(mocb200_set_boundary(dev_, ip, group, 1, boundary_[ip].get_boundary(group, 0).second),
-              "mocb200_set_boundary");
+    for (const Part &p : parts_) {
+        check(p, mocb200_set_flux(p.h, group, 1, col_.data()), "mocb200_set_flux");
+        for (int ip = p.plane_begin; ip < p.plane_end; ip++)
+            check(p, mocb200_set_boundary(p.h, ip, group, 1, boundary_[ip].get_boundary(group, 0).second),
+                  "mocb200_set_boundary");
+    }
 }
 
 void CudaMoCSweeper::download_flux(int group)
 {
-    check(mocb200_get_flux(dev_, group, 1, col_.data()), "mocb200_get_flux");
-    for (int ireg = 0; ireg < (int)n_reg_; ireg++)
-        flux_(ireg, group) = col_[ireg];
+    for (const Part &p : parts_) {
+        check(p, mocb200_get_flux(p.h, group, 1, col_.data()), "mocb200_get_flux");
+        for (int ireg = p.reg_lo; ireg < p.reg_hi; ireg++)
+            flux_(ireg, group) = col_[ireg];
+    }
 }
 
 // Device results of one group -> host objects the rest of MOCC reads.
 void CudaMoCSweeper::download_group(int group, int tally)
 {
     download_flux(group);
-    for (int ip = 0; ip < n_macroplane_; ip++)
-        check(mocb200_get_boundary(dev_, ip, group, 1, boundary_[ip].get_boundary(group, 0).second),
-              "mocb200_get_boundary");
+    for (const Part &p : parts_)
+        for (int ip = p.plane_begin; ip < p.plane_end; ip++)
+            check(p, mocb200_get_boundary(p.h, ip, group, 1, boundary_[ip].get_boundary(group, 0).second),
+                  "mocb200_get_boundary");
     if (tally != MOCB200_TALLY_NONE) {
         // moc_sweeper.cpp:208-215: zero the radial data, tally, flag; the raw device tallies
         // then go through the reference's own post_sweep (sub-plane expansion and division
         // by the surface area, moc_current_worker.hpp:272-318) so every quirk is kept.
         coarse_data_->zero_data_radial(group);
-        check(mocb200_get_coarse(dev_, group, cur_.data(), sflux_.data()), "mocb200_get_coarse");
-        for (int ip = 0; ip < n_macroplane_; ip++) {
-            for (int s = mesh_.plane_surf_xy_begin(ip); s < (int)mesh_.plane_surf_end(ip); s++) {
-                coarse_data_->current(s, group)      = cur_[s];
-                coarse_data_->surface_flux(s, group) = sflux_[s];
+        for (const Part &p : parts_) {
+            check(p, mocb200_get_coarse(p.h, group, cur_.data(), sflux_.data()), "mocb200_get_coarse");
+            for (int ip = p.plane_begin; ip < p.plane_end; ip++) {
+                for (int s = mesh_.plane_surf_xy_begin(ip); s < (int)mesh_.plane_surf_end(ip); s++) {
+                    coarse_data_->current(s, group)      = cur_[s];
+                    coarse_data_->surface_flux(s, group) = sflux_[s];
+                }
             }
         }
         moc::Current cw(coarse_data_, &mesh_);
@@ -175,24 +232,32 @@ void CudaMoCSweeper::sweep(int group)
     upload_group(group);
     const int tally = tally_mode();
     auto run = [&](int g0, int gc) {
-        double ms = 0.0;
+        // every mocb200_sweep only enqueues work on its device's stream: the GPUs sweep concurrently
         if (split_last_inner() && tally != MOCB200_TALLY_NONE) {
             // the host refreshes data between the plain inners and the tallying one
             if (n_inner_ > 1) {
-                check(mocb200_sweep(dev_, g0, gc, (int)n_inner_ - 1, MOCB200_TALLY_NONE, 0), "mocb200_sweep");
+                for (const Part &p : parts_)
+                    check(p, mocb200_sweep(p.h, g0, gc, (int)n_inner_ - 1, MOCB200_TALLY_NONE, 0), "mocb200_sweep");
                 for (int ig = g0; ig < g0 + gc; ig++)
                     download_flux(ig);
             }
             for (int ig = g0; ig < g0 + gc; ig++)
                 before_last_inner(ig);
-            check(mocb200_sweep(dev_, g0, gc, 1, tally, 0), "mocb200_sweep");
+            for (const Part &p : parts_)
+                check(p, mocb200_sweep(p.h, g0, gc, 1, tally, 0), "mocb200_sweep");
         } else {
-            check(mocb200_sweep(dev_, g0, gc, (int)n_inner_, tally, 0), "mocb200_sweep");
+            for (const Part &p : parts_)
+                check(p, mocb200_sweep(p.h, g0, gc, (int)n_inner_, tally, 0), "mocb200_sweep");
         }
         for (int ig = g0; ig < g0 + gc; ig++)
             download_group(ig, tally);
-        if (mocb200_last_sweep_ms(dev_, &ms) == MOCB200_OK)
-            device_sweep_ms_ += ms * n_inner_; // last inner timed; inners are alike
+        double ms_max = 0.0;
+        for (const Part &p : parts_) {
+            double ms = 0.0;
+            if (mocb200_last_sweep_ms(p.h, &ms) == MOCB200_OK)
+                ms_max = std::max(ms_max, ms);
+        }
+        device_sweep_ms_ += ms_max * n_inner_; // last inner timed; inners are alike; slowest GPU counts
     };
     if (!group_batch_)
         run(group, 1);
@@ -256,7 +321,8 @@ void CudaMoCSweeper2D3D::before_last_inner(int group)
     for (int ip = 0; ip < n_macroplane_; ip++)
         for (int ic = 0; ic < ncp; ic++)
             sn_col_[(size_t)ip * ncp + ic] = xstr_sn_[ic + plane_xs_offset_[ip]];
-    check(mocb200_set_sn_xs(dev_, group, 1, sn_col_.data()), "mocb200_set_sn_xs");
+    for (const Part &p : parts_)
+        check(p, mocb200_set_sn_xs(p.h, group, 1, sn_col_.data()), "mocb200_set_sn_xs");
 }
 
 // Device correction factors -> CorrectionData, with the residual bookkeeping of
@@ -265,7 +331,8 @@ void CudaMoCSweeper2D3D::post_group(int group, int tally)
 {
     if (tally != MOCB200_TALLY_CORRECTIONS)
         return;
-    check(mocb200_get_corrections(dev_, group, alpha_.data(), beta_.data()), "mocb200_get_corrections");
+    for (const Part &p : parts_) // each handle fills the cells of its own macroplanes
+        check(p, mocb200_get_corrections(p.h, group, alpha_.data(), beta_.data()), "mocb200_get_corrections");
     const int ncp       = mesh_.nx() * mesh_.ny();
     const size_t n_cell = (size_t)n_macroplane_ * ncp;
     const int n_ang     = ang_quad_.ndir() / 4; // sweep angles (octants 1-2)

@@ -13,7 +13,8 @@
 //
 // Options live on a <cuda> child of <sweeper> so that the reference's attribute validation
 // (moc_sweeper.cpp:54-57, util/validate_input.cpp:24-42) stays quiet:
-//   <cuda device="0" group_batch="f" kernel="track" max_polar="2"/>
+//   <cuda device="0" group_batch="f" kernel="auto" max_polar="2"/>      one GPU
+//   <cuda devices="0,1,2,3" .../>                                       macroplanes sharded over several GPUs
 //     group_batch="t": sweep(0..ng-2) only stage their sources; sweep(ng-1) sweeps all groups
 //                      in one batch (Jacobi instead of Gauss-Seidel in energy: same converged
 //                      answer, different iteration path).
@@ -70,12 +71,18 @@ protected:
     }
     void download_flux(int group);
 
-    void check(int rc, const char *what) const;
+    // One C-ABI handle per GPU, each owning a contiguous range of macroplanes (planes are independent
+    // inside a sweep, moc_sweeper_kernel.inc.hpp:51-153); a single device owns all of them.
+    struct Part {
+        mocb200_sweeper *h = nullptr;
+        int device = 0, plane_begin = 0, plane_end = 0, reg_lo = 0, reg_hi = 0;
+    };
+    void check(const Part &p, int rc, const char *what) const;
     void upload_group(int group);
     void download_group(int group, int tally);
 
-    mocb200_sweeper *dev_ = nullptr;
-    bool group_batch_     = false;
+    std::vector<Part> parts_;
+    bool group_batch_ = false;
     int n_bc_             = 0; // boundary values per group per plane
     int n_macroplane_     = 0;
     // per-FSR cross sections, [n_group][n_reg]

@@ -72,3 +72,15 @@ def test_2d3d_solve_matches_reference(tmp_path):
     """The reference's PlaneSweeper_2D3D around the CUDA MoC sweeper: k history of 12 outers and the MoC flux."""
     res = _solve(tmp_path, "mini2d3d.xml", ["solver/sweeper@type=2d3d_cuda"])
     _check(res, _golden("mini2d3d_solve_ref.arrays.gz"), k_tol=1e-8, flux_tol=1e-7)
+
+
+@pytest.mark.parametrize("devices", ["0,0", "0,1"])
+def test_2d3d_planes_sharded_over_handles(tmp_path, devices):
+    """Macroplanes split over two C-ABI handles (two GPUs when the box has them, else twice the same GPU):
+    identical results to the single-handle run, because planes are independent inside a sweep."""
+    import torch
+    if devices == "0,1" and torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    res = _solve(tmp_path, "mini2d3d.xml",
+                 ["solver/sweeper@type=2d3d_cuda", f"solver/sweeper/moc_sweeper/cuda@devices={devices}"])
+    _check(res, _golden("mini2d3d_solve_ref.arrays.gz"), k_tol=1e-8, flux_tol=1e-7)
