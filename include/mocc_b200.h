@@ -59,10 +59,11 @@ extern "C" {
                                   factor tables (<= 2 ulp from the table entries) */
 
 /* sweep kernel selection (diagnostics / A-B measurements) */
-#define MOCB200_KERNEL_AUTO 0   /* CACHED when the attenuation cache fits in device memory, else TRACK */
+#define MOCB200_KERNEL_AUTO 0   /* CHUNK when the attenuation cache fits in device memory, else TRACK */
 #define MOCB200_KERNEL_ITEM 1   /* one thread per (track, direction, group), serial walk */
 #define MOCB200_KERNEL_TRACK 2  /* one warp per track, both directions, affine scan over lanes */
 #define MOCB200_KERNEL_CACHED 3 /* TRACK with the table lookups cached in HBM per cross-section upload */
+#define MOCB200_KERNEL_CHUNK 4  /* CACHED with one scan per track: TMA-staged track, lane-owned contiguous chunks */
 
 /*
  * Flattened ray-tracing data ("MOCFLAT"), produced once on the host from the
@@ -158,7 +159,9 @@ typedef struct mocb200_options {
     int32_t plane_begin;     /* this rank's macroplane range [plane_begin, plane_end); both 0 = all */
     int32_t plane_end;
     int32_t kernel;          /* MOCB200_KERNEL_* */
-    int32_t reserved[8];
+    int32_t chunk_cap;       /* CHUNK kernel: cap on the segments a warp stages at once (0 = what fits); test hook
+                                for the super-block chaining of long tracks */
+    int32_t reserved[7];
 } mocb200_options;
 
 /* Build the device-resident problem. The host arrays may be freed afterwards. */

@@ -4,6 +4,7 @@
 #include "mocc_b200.h"
 
 #include <algorithm>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -12,6 +13,7 @@
 
 #include "moc_kernels.cuh"
 #include "moc_sweep_kernel.cuh"
+#include "moc_chunk_kernel.cuh"
 
 using namespace mocb200;
 
@@ -32,6 +34,8 @@ struct TrackList { // one launch of the track kernel: units of one (unique plane
     int32_t n_planes   = 0;
     int64_t segs       = 0; // reference segments (polar copies counted) swept per group, all planes
     int64_t pseg       = 0; // padded segments of all units (cache positions)
+    int32_t max_nseg   = 0; // longest track of the list
+    ChunkUnit *d_cunits = nullptr; // self-contained descriptors of the same units (chunk kernel)
     double *d_cache    = nullptr; // attenuation cache of this list (CACHED kernel)
 };
 
@@ -361,7 +365,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
 
     // ---- track kernel: padded geometry, crossing lists with sentinels, per-4-segment crossing pointers ----
     h->kernel = opt.kernel;
-    if (h->kernel < MOCB200_KERNEL_AUTO || h->kernel > MOCB200_KERNEL_CACHED)
+    if (h->kernel < MOCB200_KERNEL_AUTO || h->kernel > MOCB200_KERNEL_CHUNK)
         return fail(h, MOCB200_ERR_INVALID, "unknown kernel selection %d", h->kernel);
     {
         std::vector<int64_t> pbegin(p.n_trk + 1, 0);
@@ -454,6 +458,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                     }
                     tl.unique = u, tl.phase = phase, tl.np = np;
                     tl.n_units  = (int32_t)units.size();
+                    tl.max_nseg = units.front().nseg;
                     tl.n_planes = (int32_t)planes.size();
                     int64_t segs = 0;
                     for (const auto &tu : units)
@@ -463,6 +468,31 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                         return fail(h, MOCB200_ERR_INVALID, "track list too large for 32-bit scheduling");
                     if ((rc2 = dev_upload(h, &tl.d_units, units)) || (rc2 = dev_upload(h, &tl.d_planes, planes)))
                         return rc2;
+                    {
+                        // chunk-kernel descriptors: boundary linkage resolved once (boundary_condition.cpp:155-191)
+                        std::vector<ChunkUnit> cu(units.size());
+                        for (size_t i = 0; i < units.size(); i++) {
+                            const TrackUnit &tu = units[i];
+                            ChunkUnit &c = cu[i];
+                            c.seg_begin = tu.seg_begin, c.nseg = tu.nseg, c.cpos = tu.cpos, c.pad = 0;
+                            for (int q = 0; q < kMaxPolar; q++) {
+                                const int ang = bundles[tu.bundle].ang[q];
+                                c.ang[q]  = ang;
+                                c.in_f[q] = p.bc_offset[ang] + tu.bc0;
+                                c.in_b[q] = p.bc_offset[ang + p.n_ang] + tu.bc1;
+                                for (int dir = 0; dir < 2; dir++) {
+                                    const int ao = ang + dir * p.n_ang, out_slot = dir ? tu.bc0 : tu.bc1;
+                                    const int sx = p.bc_size_x[ao], face = out_slot >= sx ? 1 : 0;
+                                    const int kind = p.bc_dst_kind[2 * ao + face];
+                                    const int dst  = p.bc_dst_off[2 * ao + face] + out_slot - (face ? sx : 0);
+                                    const int32_t enc = kind == 2 ? INT32_MIN : (kind == 1 ? dst : -(dst + 1));
+                                    (dir ? c.out_b : c.out_f)[q] = enc;
+                                }
+                            }
+                        }
+                        if ((rc2 = dev_upload(h, &tl.d_cunits, cu)))
+                            return rc2;
+                    }
                     h->tlists.push_back(tl);
                 }
             }
@@ -634,7 +664,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     h->cache_valid.assign(p.n_group, false);
     if ((rc = dev_alloc(h, &h->d_qg, (size_t)p.n_group * p.n_reg)) || (rc = dev_alloc(h, &h->d_tg, (size_t)p.n_group * p.n_reg)))
         return rc;
-    if (h->kernel == MOCB200_KERNEL_AUTO || h->kernel == MOCB200_KERNEL_CACHED) {
+    if (h->kernel == MOCB200_KERNEL_AUTO || h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK) {
         // the attenuation cache: 8 bytes per (padded segment, polar angle, group, plane)
         int64_t bytes = 0;
         for (const auto &tl : h->tlists)
@@ -642,10 +672,10 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
         const bool fits = (double)bytes < 0.8 * (double)free_b;
-        if (!fits && h->kernel == MOCB200_KERNEL_CACHED)
+        if (!fits && h->kernel != MOCB200_KERNEL_AUTO)
             return fail(h, MOCB200_ERR_INVALID, "attenuation cache (%lld MiB) does not fit in device memory",
                         (long long)(bytes >> 20));
-        h->kernel = fits ? MOCB200_KERNEL_CACHED : MOCB200_KERNEL_TRACK;
+        h->kernel = !fits ? MOCB200_KERNEL_TRACK : (h->kernel == MOCB200_KERNEL_CACHED ? MOCB200_KERNEL_CACHED : MOCB200_KERNEL_CHUNK);
     }
     h->stats.device_bytes = h->device_bytes;
     return MOCB200_OK;
@@ -694,6 +724,33 @@ WarpFn pick_warp_kernel(int gl, int np, int tally, bool cached)
     if (cached)
         return gl == 1 ? pick_warp_gl<1, true>(np, tally) : pick_warp_gl<8, true>(np, tally);
     return gl == 1 ? pick_warp_gl<1, false>(np, tally) : pick_warp_gl<8, false>(np, tally);
+}
+
+typedef void (*ChunkFn)(const ChunkArgs);
+
+ChunkFn pick_chunk_kernel(int np)
+{
+    switch (np) {
+    case 1: return sweep_chunk_kernel<1>;
+    case 2: return sweep_chunk_kernel<2>;
+    case 3: return sweep_chunk_kernel<3>;
+    case 4: return sweep_chunk_kernel<4>;
+    }
+    return nullptr;
+}
+
+constexpr int kChunkSmemBudget = 232448 - 1024; // opt-in dynamic shared memory per CTA minus the static part
+
+// shared-memory capacity (segments per warp, 32 x odd) and warps per CTA of the chunk kernel for a list
+void chunk_geometry(int max_nseg, int np, int cap_opt, int *caps, int *warps)
+{
+    const int cap_limit = 32 * ((((kChunkSmemBudget / 5) / (8 * (np + 2) + 8)) / 32 - 1) | 1); // >= 5 warps per CTA
+    int c = 32 * (((max_nseg + 31) / 32) | 1);
+    c = std::min(c, cap_limit);
+    if (cap_opt > 0)
+        c = std::min(c, 32 * (((cap_opt + 31) / 32) | 1));
+    *caps  = c;
+    *warps = std::max(1, std::min<int>(kChunkMaxWarps, kChunkSmemBudget / (int)chunk_warp_bytes(c, np)));
 }
 
 int track_smem_bytes(const mocb200_sweeper *h)
@@ -804,7 +861,11 @@ int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb
                 return MOCB200_ERR_CUDA;
             }
         }
-    e = cudaFuncSetAttribute((const void *)exp_cache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int np = 1; np <= kMaxPolar && e == cudaSuccess; np++)
+        e = cudaFuncSetAttribute((const void *)pick_chunk_kernel(np), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kChunkSmemBudget);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute((const void *)exp_cache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
         fail(nullptr, MOCB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         mocb200_destroy(h);
@@ -981,7 +1042,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
 
     const int gl          = g_count <= 2 ? 1 : 8; // group lanes per segment (track / cached kernels)
     const int n_gsets     = (g_count + gl - 1) / gl;
-    const bool cached     = h->kernel == MOCB200_KERNEL_CACHED;
+    const bool cached     = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK;
     const bool group_major = cached && gl == 1;
 
     if (cached) {
@@ -1142,8 +1203,23 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
                 a.cache = tl.d_cache, a.list_pseg = tl.pseg, a.cache_groups = h->G;
                 a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
-                pick_warp_kernel(gl, tl.np, tally, cached)<<<grid, kWarpBlock, cached ? 0 : track_smem_bytes(h),
-                                                             h->stream>>>(a);
+                if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1 && tally == MOCB200_TALLY_NONE) {
+                    int caps = 0, cw = 0;
+                    chunk_geometry(tl.max_nseg, tl.np, h->opt.chunk_cap, &caps, &cw);
+                    const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((warps + cw - 1) / cw, h->track_grid));
+                    ChunkArgs c{};
+                    c.units = tl.d_cunits, c.n_units = tl.n_units, c.counter = counter;
+                    c.planes = tl.d_planes, c.n_planes = tl.n_planes, c.seg_fsr = h->d_pseg_fsr, c.wt_v_st = h->d_wt;
+                    c.plane_first_reg = h->d_plane_first_reg, c.n_ang = h->n_ang, c.bc_per_group = h->bcpg;
+                    c.g_begin = g_begin, c.g_count = g_count, c.GP = h->GP, c.n_reg = h->n_reg;
+                    c.q = h->d_qg, c.tally = h->d_tg, c.bc_in = bc_in, c.bc_out = bc_out;
+                    c.scratch = h->d_scratch, c.scratch_per_warp = h->scratch_per_warp;
+                    c.cache = tl.d_cache, c.list_pseg = tl.pseg, c.cache_groups = h->G, c.caps = caps;
+                    pick_chunk_kernel(tl.np)<<<cgrid, 32 * cw, cw * chunk_warp_bytes(caps, tl.np), h->stream>>>(c);
+                } else {
+                    pick_warp_kernel(gl, tl.np, tally, cached)<<<grid, kWarpBlock, cached ? 0 : track_smem_bytes(h),
+                                                                 h->stream>>>(a);
+                }
                 h->stats.kernel_launches++;
                 h->stats.sweep_launches++;
             }

@@ -48,6 +48,8 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
         opt.kernel = MOCB200_KERNEL_CACHED;
     else if (kernel == "item")
         opt.kernel = MOCB200_KERNEL_ITEM;
+    else if (kernel == "chunk")
+        opt.kernel = MOCB200_KERNEL_CHUNK;
     else
         throw EXCEPT("Unrecognized <cuda kernel=...> option.");
     if (allow_splitting_ && group_batch_)

@@ -64,7 +64,7 @@ def _xy_mask(flat):
 
 @pytest.mark.parametrize("case", [c for c in sorted(CASES) if c != "mini3d_2d3d"])
 @pytest.mark.parametrize("max_polar", [1, 2, 4])
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 def test_sweep1g_matches_reference_golden(case, max_polar, kernel):
     flat, gold = load_case(case)
     gs = bool(gold["gs_boundary"][0])
@@ -78,6 +78,25 @@ def test_sweep1g_matches_reference_golden(case, max_polar, kernel):
             area = flat["surf_area"]
             _close(cur[xy] / area[xy], rec["current"][xy], atol=1e-13)
             _close(sf[xy] / area[xy], rec["surface_flux"][xy], atol=1e-13)
+    sw.close()
+
+
+@pytest.mark.parametrize("case", ["mini2d_gs", "mini2d_jacobi", "mini3d_gs", "3x3_s05_gs"])
+@pytest.mark.parametrize("max_polar", [1, 2, 3])
+def test_chunk_kernel_superblocks_match_reference_golden(case, max_polar):
+    """CHUNK kernel with a 32-segment staging cap: every longer track is chained through super-blocks."""
+    flat, gold = load_case(case)
+    gs = bool(gold["gs_boundary"][0])
+    sw = _sweeper(flat, boundary_update=0 if gs else 1, max_polar=max_polar, kernel=4, chunk_cap=32)
+    n = 0
+    for rec in records(gold):
+        if int(rec["mode"][0]) != 0:
+            continue
+        flux, bc_out, _, _ = _run_record(sw, flat, rec)
+        _close(flux, rec["flux_out"])
+        _close(bc_out, rec["bc_out"])
+        n += 1
+    assert n > 0
     sw.close()
 
 
