@@ -159,8 +159,8 @@ typedef struct mocb200_options {
     int32_t plane_begin;     /* this rank's macroplane range [plane_begin, plane_end); both 0 = all */
     int32_t plane_end;
     int32_t kernel;          /* MOCB200_KERNEL_* */
-    int32_t chunk_cap;       /* CHUNK kernel: cap on the segments a warp stages at once (0 = what fits); test hook
-                                for the super-block chaining of long tracks */
+    int32_t chunk_cap;       /* CHUNK kernel test hook: cap on the segments staged at once (0 = what fits), forces the
+                                super-block chaining of long tracks; negative = that cap with two-warp teams */
     int32_t reserved[7];
 } mocb200_options;
 

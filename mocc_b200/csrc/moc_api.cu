@@ -7,6 +7,7 @@
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -36,6 +37,7 @@ struct TrackList { // one launch of the track kernel: units of one (unique plane
     int64_t pseg       = 0; // padded segments of all units (cache positions)
     int32_t max_nseg   = 0; // longest track of the list
     ChunkUnit *d_cunits = nullptr; // self-contained descriptors of the same units (chunk kernel)
+    int2 *d_pinfo       = nullptr; // per plane of the list: {macroplane, first FSR}
     double *d_cache    = nullptr; // attenuation cache of this list (CACHED kernel)
 };
 
@@ -490,7 +492,10 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                                 }
                             }
                         }
-                        if ((rc2 = dev_upload(h, &tl.d_cunits, cu)))
+                        std::vector<int2> pinfo;
+                        for (int32_t ip : planes)
+                            pinfo.push_back(make_int2(ip, p.plane_first_reg[ip]));
+                        if ((rc2 = dev_upload(h, &tl.d_cunits, cu)) || (rc2 = dev_upload(h, &tl.d_pinfo, pinfo)))
                             return rc2;
                     }
                     h->tlists.push_back(tl);
@@ -728,29 +733,39 @@ WarpFn pick_warp_kernel(int gl, int np, int tally, bool cached)
 
 typedef void (*ChunkFn)(const ChunkArgs);
 
-ChunkFn pick_chunk_kernel(int np)
+ChunkFn pick_chunk_kernel(int np, int nw)
 {
-    switch (np) {
-    case 1: return sweep_chunk_kernel<1>;
-    case 2: return sweep_chunk_kernel<2>;
-    case 3: return sweep_chunk_kernel<3>;
-    case 4: return sweep_chunk_kernel<4>;
+    switch (np * 2 + (nw == 2 ? 1 : 0)) {
+    case 2: return sweep_chunk_kernel<1, 1>;
+    case 3: return sweep_chunk_kernel<1, 2>;
+    case 4: return sweep_chunk_kernel<2, 1>;
+    case 5: return sweep_chunk_kernel<2, 2>;
+    case 6: return sweep_chunk_kernel<3, 1>;
+    case 7: return sweep_chunk_kernel<3, 2>;
+    case 8: return sweep_chunk_kernel<4, 1>;
+    case 9: return sweep_chunk_kernel<4, 2>;
     }
     return nullptr;
 }
 
-constexpr int kChunkSmemBudget = 232448 - 1024; // opt-in dynamic shared memory per CTA minus the static part
+constexpr int kChunkSmemBudget = 232448 - 12288; // opt-in dynamic shared memory per CTA minus the static part
 
-// shared-memory capacity (segments per warp, 32 x odd) and warps per CTA of the chunk kernel for a list
-void chunk_geometry(int max_nseg, int np, int cap_opt, int *caps, int *warps)
+// launch geometry of the chunk kernel for a list: segments a team stages at once, warps per team,
+// teams per CTA
+void chunk_geometry(int max_nseg, int np, int cap_opt, int *caps, int *nw, int *teams)
 {
-    const int cap_limit = 32 * ((((kChunkSmemBudget / 5) / (8 * (np + 2) + 8)) / 32 - 1) | 1); // >= 5 warps per CTA
-    int c = 32 * (((max_nseg + 31) / 32) | 1);
+    const int per_seg   = 8 * (np + 2) + 8;
+    const int cap_limit = ((kChunkSmemBudget / 4) / per_seg) & ~31; // at least 4 tracks in flight per SM
+    int c = (max_nseg + 31) & ~31;
     c = std::min(c, cap_limit);
     if (cap_opt > 0)
-        c = std::min(c, 32 * (((cap_opt + 31) / 32) | 1));
+        c = std::min(c, (cap_opt + 31) & ~31);
     *caps  = c;
-    *warps = std::max(1, std::min<int>(kChunkMaxWarps, kChunkSmemBudget / (int)chunk_warp_bytes(c, np)));
+    *nw    = c >= 256 ? 2 : 1;
+    static const char *force_nw = getenv("MOCB200_CHUNK_NW"); // tuning hook: warps per track (1 or 2)
+    if (force_nw && (force_nw[0] == '1' || force_nw[0] == '2'))
+        *nw = force_nw[0] - '0';
+    *teams = std::max(1, std::min<int>(kChunkMaxWarps / *nw, kChunkSmemBudget / (int)chunk_warp_bytes(c, np)));
 }
 
 int track_smem_bytes(const mocb200_sweeper *h)
@@ -862,8 +877,9 @@ int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb
             }
         }
     for (int np = 1; np <= kMaxPolar && e == cudaSuccess; np++)
-        e = cudaFuncSetAttribute((const void *)pick_chunk_kernel(np), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kChunkSmemBudget);
+        for (int nw = 1; nw <= kChunkMaxTeam && e == cudaSuccess; nw++)
+            e = cudaFuncSetAttribute((const void *)pick_chunk_kernel(np, nw), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kChunkSmemBudget);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute((const void *)exp_cache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -1204,18 +1220,23 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 a.cache = tl.d_cache, a.list_pseg = tl.pseg, a.cache_groups = h->G;
                 a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
                 if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1 && tally == MOCB200_TALLY_NONE) {
-                    int caps = 0, cw = 0;
-                    chunk_geometry(tl.max_nseg, tl.np, h->opt.chunk_cap, &caps, &cw);
-                    const int cgrid = (int)std::max<int64_t>(1, std::min<int64_t>((warps + cw - 1) / cw, h->track_grid));
+                    int caps = 0, nw = 1, teams = 1;
+                    chunk_geometry(tl.max_nseg, tl.np, h->opt.chunk_cap, &caps, &nw, &teams);
+                    if (h->opt.chunk_cap < 0) // test hook: negative cap = that cap with two-warp teams
+                        chunk_geometry(tl.max_nseg, tl.np, -h->opt.chunk_cap, &caps, &nw, &teams), nw = 2,
+                            teams = std::min(teams, kChunkMaxWarps / 2);
+                    const int cgrid =
+                        (int)std::max<int64_t>(1, std::min<int64_t>((warps + teams - 1) / teams, h->track_grid));
                     ChunkArgs c{};
                     c.units = tl.d_cunits, c.n_units = tl.n_units, c.counter = counter;
-                    c.planes = tl.d_planes, c.n_planes = tl.n_planes, c.seg_fsr = h->d_pseg_fsr, c.wt_v_st = h->d_wt;
-                    c.plane_first_reg = h->d_plane_first_reg, c.n_ang = h->n_ang, c.bc_per_group = h->bcpg;
+                    c.pinfo = tl.d_pinfo, c.n_planes = tl.n_planes, c.seg_fsr = h->d_pseg_fsr, c.wt_v_st = h->d_wt;
+                    c.n_ang = h->n_ang, c.bc_per_group = h->bcpg;
                     c.g_begin = g_begin, c.g_count = g_count, c.GP = h->GP, c.n_reg = h->n_reg;
                     c.q = h->d_qg, c.tally = h->d_tg, c.bc_in = bc_in, c.bc_out = bc_out;
                     c.scratch = h->d_scratch, c.scratch_per_warp = h->scratch_per_warp;
                     c.cache = tl.d_cache, c.list_pseg = tl.pseg, c.cache_groups = h->G, c.caps = caps;
-                    pick_chunk_kernel(tl.np)<<<cgrid, 32 * cw, cw * chunk_warp_bytes(caps, tl.np), h->stream>>>(c);
+                    pick_chunk_kernel(tl.np, nw)<<<cgrid, 32 * nw * teams, teams * chunk_warp_bytes(caps, tl.np),
+                                                   h->stream>>>(c);
                 } else {
                     pick_warp_kernel(gl, tl.np, tally, cached)<<<grid, kWarpBlock, cached ? 0 : track_smem_bytes(h),
                                                                  h->stream>>>(a);

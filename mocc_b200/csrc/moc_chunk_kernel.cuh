@@ -38,7 +38,8 @@
 
 namespace mocb200 {
 
-constexpr int kChunkMaxWarps = 12; // 384 threads: up to 170 registers per thread (occupancy is shared-memory bound)
+constexpr int kChunkMaxWarps = 14; // 448 threads: up to 146 registers per thread (occupancy is shared-memory bound)
+constexpr int kChunkMaxTeam  = 2;  // warps cooperating on one track
 
 // One (track, polar bundle) of the chunk kernel: everything a warp needs to start the track in ONE
 // dependent load (the boundary linkage of BoundaryCondition::update, boundary_condition.cpp:155-191,
@@ -68,6 +69,10 @@ __device__ __forceinline__ void cp_async_8(void *dst_smem, const void *src_gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -90,37 +95,11 @@ template <int P> __device__ __forceinline__ void load_ex(const double *exb, int 
 }
 
 
-// composite affine map of the lane's chunk for the backward direction only (pass A of long tracks)
+// composite affine maps of the lane's chunk: A (both directions), Bf (forward), Bb (backward)
 template <int P>
-__device__ __forceinline__ void chunk_compose_bwd(const double *exb, const double *qb, int lo, int hi, double (&A)[P],
-                                                  double (&B)[P])
+__device__ __forceinline__ void chunk_compose(const double *exb, const double *qb, int lo, int hi, double (&A)[P],
+                                              double (&Bf)[P], double (&Bb)[P])
 {
-#pragma unroll
-    for (int p = 0; p < P; p++)
-        A[p] = 1.0, B[p] = 0.0;
-    for (int k = lo; k < hi; k++) {
-        double e[P];
-        load_ex<P>(exb, k, e);
-        const double q = qb[k];
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-            const double bq = q * (1.0 - e[p]);
-            B[p] = fma(A[p], bq, B[p]); // M o m_k: the backward sweep applies the higher segment first
-            A[p] *= e[p];
-        }
-    }
-}
-
-// One staged (super-)block: compose the lane chunks, scan, walk both directions. On entry cf is the
-// forward flux entering the block and eb the backward flux entering it (from the far side); on exit cf
-// is the forward flux leaving the block, psi_b (lane 0) the backward flux leaving it, and ab[k] holds
-// the summed tally contribution of segment k.
-template <int P>
-__device__ __forceinline__ void chunk_block(const double *exb, const double *qb, double *ab, int lane, int lo, int hi,
-                                            const double (&wt)[P], double (&cf)[P], const double (&eb)[P],
-                                            double (&psi_b)[P])
-{
-    double A[P], Bf[P], Bb[P];
 #pragma unroll
     for (int p = 0; p < P; p++)
         A[p] = 1.0, Bf[p] = 0.0, Bb[p] = 0.0;
@@ -132,49 +111,48 @@ __device__ __forceinline__ void chunk_block(const double *exb, const double *qb,
 #pragma unroll
         for (int p = 0; p < P; p++) {
             const double bq = q * (1.0 - e[p]);
-            Bb[p] = fma(A[p], bq, Bb[p]); // M o m_k
+            Bb[p] = fma(A[p], bq, Bb[p]); // M o m_k: the backward sweep applies the higher segment first
             Bf[p] = fma(e[p], Bf[p], bq); // m_k o M
             A[p] *= e[p];
         }
     }
-    // ---- one inclusive scan over the lanes: prefix (forward), suffix (backward) ----
-    double psi_f[P];
-    {
-        double Af[P], Ab[P];
+}
+
+// inclusive scans over the 32 lanes of a warp: (Af, Bf) prefix (forward), (Ab, Bb) suffix (backward)
+template <int P>
+__device__ __forceinline__ void chunk_scan(int lane, const double (&A)[P], double (&Af)[P], double (&Bf)[P],
+                                           double (&Ab)[P], double (&Bb)[P])
+{
 #pragma unroll
-        for (int p = 0; p < P; p++)
-            Af[p] = A[p], Ab[p] = A[p];
+    for (int p = 0; p < P; p++)
+        Af[p] = A[p], Ab[p] = A[p];
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-#pragma unroll
-            for (int p = 0; p < P; p++) {
-                const double Ae = __shfl_up_sync(0xffffffffu, Af[p], s);
-                const double Be = __shfl_up_sync(0xffffffffu, Bf[p], s);
-                const double Ah = __shfl_down_sync(0xffffffffu, Ab[p], s);
-                const double Bh = __shfl_down_sync(0xffffffffu, Bb[p], s);
-                if (lane >= s) { // mine o earlier
-                    Bf[p] = fma(Af[p], Be, Bf[p]);
-                    Af[p] *= Ae;
-                }
-                if (lane + s < 32) { // mine o higher
-                    Bb[p] = fma(Ab[p], Bh, Bb[p]);
-                    Ab[p] *= Ah;
-                }
-            }
-        }
+    for (int s = 1; s < 32; s <<= 1) {
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            const double out_f = fma(Af[p], cf[p], Bf[p]); // flux leaving this lane's chunk, forward
-            const double out_b = fma(Ab[p], eb[p], Bb[p]); // ... backward
-            const double in_f  = __shfl_up_sync(0xffffffffu, out_f, 1);
-            const double in_b  = __shfl_down_sync(0xffffffffu, out_b, 1);
-            psi_f[p] = lane == 0 ? cf[p] : in_f;
-            psi_b[p] = lane == 31 ? eb[p] : in_b;
-            cf[p]    = __shfl_sync(0xffffffffu, out_f, 31); // carried to the next super-block
+            const double Ae = __shfl_up_sync(0xffffffffu, Af[p], s);
+            const double Be = __shfl_up_sync(0xffffffffu, Bf[p], s);
+            const double Ah = __shfl_down_sync(0xffffffffu, Ab[p], s);
+            const double Bh = __shfl_down_sync(0xffffffffu, Bb[p], s);
+            if (lane >= s) { // mine o earlier
+                Bf[p] = fma(Af[p], Be, Bf[p]);
+                Af[p] *= Ae;
+            }
+            if (lane + s < 32) { // mine o higher
+                Bb[p] = fma(Ab[p], Bh, Bb[p]);
+                Ab[p] *= Ah;
+            }
         }
     }
-    // ---- walk the chunk in both directions like the reference loop (kernel:103-129); the two walks
-    //      are independent dependency chains and meet in the middle of the chunk ----
+}
+
+// walk the chunk in both directions like the reference loop (kernel:103-129); the two walks are
+// independent dependency chains and meet in the middle of the chunk. ab[k] receives the summed tally
+// contribution of segment k (both directions, all polar angles).
+template <int P>
+__device__ __forceinline__ void chunk_walk(const double *exb, const double *qb, double *ab, int lo, int hi,
+                                           const double (&wt)[P], double (&psi_f)[P], double (&psi_b)[P])
+{
     int kf = lo, kb = hi - 1;
     for (; kf < kb; ++kf, --kb) { // first visit of both segments
         double ef[P], er[P];
@@ -235,152 +213,258 @@ struct ChunkArgs {
     const ChunkUnit *units;
     int32_t n_units;
     uint32_t *counter;
-    const int32_t *planes;
+    const int2 *pinfo; // per plane of the list: {macroplane, its first FSR}
     int32_t n_planes;
     const int32_t *seg_fsr; // padded FSR ids
     const double *wt_v_st;  // [n_plane][n_ang]
-    const int32_t *plane_first_reg;
     int32_t n_ang, bc_per_group;
     int32_t g_begin, g_count, GP, n_reg;
     const double *q; // group-major [g - g_begin][n_reg]
     double *tally;   // same layout
     const double *bc_in;
     double *bc_out;
-    double *scratch; // per warp: backward flux entering each super-block of a long track
+    double *scratch; // per team: backward flux entering each super-block of a long track
     int32_t scratch_per_warp;
     const double *cache; // attenuation cache of this list [plane][g][pos][P]
     int64_t list_pseg;
     int32_t cache_groups;
-    int32_t caps; // segments a warp stages at once (32 x odd)
+    int32_t caps; // segments a team stages at once
 };
 
-template <int P>
+// A work item as the team sees it: filled asynchronously (cp.async) one item ahead, in shared memory
+struct __align__(16) ChunkWork {
+    ChunkUnit u;
+    int2 pinfo; // {macroplane, first FSR}
+    int32_t ipl, grel; // plane index within the list, group index within the launch
+    double wt[4], cf[4], cb[4]; // angle weights, incoming boundary flux (forward, backward)
+};
+
+// NW warps ("team") cooperate on one track: 32 NW lanes, each owning one contiguous chunk.
+template <int P, int NW>
 __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(const ChunkArgs a)
 {
+    constexpr int T = 32 * NW; // lanes of a team
     extern __shared__ __align__(16) double s_dyn[];
     __shared__ uint64_t s_bar[3 * kChunkMaxWarps];
+    __shared__ double s_tot[kChunkMaxWarps][kChunkMaxTeam][4][4]; // per team, per warp: Af, Bf, Ab, Bb of the warp's lanes
+    __shared__ uint32_t s_w[2 * kChunkMaxWarps];
+    __shared__ ChunkWork s_work[kChunkMaxWarps][2];
 
     const int caps = a.caps;
     const int lane = threadIdx.x & 31;
     const int wid  = threadIdx.x >> 5;
-    char *wbase    = reinterpret_cast<char *>(s_dyn) + (size_t)wid * chunk_warp_bytes(caps, P);
+    const int team = wid / NW, wl = wid - team * NW;
+    const int tl   = wl * 32 + lane; // lane within the team
+    const bool leader = tl == 0;
+    char *wbase    = reinterpret_cast<char *>(s_dyn) + (size_t)team * chunk_warp_bytes(caps, P);
     double *exb    = reinterpret_cast<double *>(wbase);
     double *qb     = exb + (size_t)caps * P;
     double *ab     = qb + caps;
     int32_t *fbuf  = reinterpret_cast<int32_t *>(ab + caps); // two FSR-id buffers (plane-local ids)
-    uint64_t *bar  = &s_bar[3 * wid];                        // [0], [1] FSR-id buffers, [2] attenuations
-    if (lane == 0) {
+    uint64_t *bar  = &s_bar[3 * team];                       // [0], [1] FSR-id buffers, [2] attenuations
+    auto team_sync = [&]() {
+        if (NW == 1)
+            __syncwarp();
+        else
+            asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(T) : "memory");
+    };
+    if (leader) {
         mbar_init(bar, 1);
         mbar_init(bar + 1, 1);
         mbar_init(bar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    team_sync();
     uint32_t par_f = 0u, par_e = 0u; // mbarrier phase parities (bit fi of par_f: FSR-id buffer fi)
 
     const int GP            = a.GP;
     const uint32_t per_unit = (uint32_t)a.n_planes * (uint32_t)a.g_count;
     const uint32_t total    = (uint32_t)a.n_units * per_unit;
-    const int warp_global   = blockIdx.x * (blockDim.x >> 5) + wid;
-    double *sc              = a.scratch + (size_t)warp_global * a.scratch_per_warp;
+    const int team_global   = blockIdx.x * ((blockDim.x >> 5) / NW) + team;
+    double *sc              = a.scratch + (size_t)team_global * a.scratch_per_warp;
     const int32_t *__restrict__ seg_fsr = a.seg_fsr;
 
-    auto next_work = [&]() -> uint32_t {
-        uint32_t w = 0;
-        if (lane == 0)
-            w = atomicAdd(a.counter, 1u);
-        return __shfl_sync(0xffffffffu, w, 0);
+    // ---- asynchronous two-level prefetch of a work item into its shared-memory slot ----
+    // level 1: descriptor and plane info (addresses depend on the work index only)
+    auto prefetch_unit = [&](uint32_t w, ChunkWork *k) {
+        if (wl == 0 && lane < 8) {
+            const uint32_t unit_id = w / per_unit;
+            const uint32_t r       = w - unit_id * per_unit;
+            const uint32_t ipl     = r / (uint32_t)a.g_count;
+            if (lane < 6)
+                cp_async_16(reinterpret_cast<char *>(&k->u) + 16 * lane,
+                            reinterpret_cast<const char *>(a.units + unit_id) + 16 * lane);
+            else if (lane == 6)
+                cp_async_8(&k->pinfo, a.pinfo + ipl);
+            else
+                k->ipl = (int)ipl, k->grel = (int)(r - ipl * (uint32_t)a.g_count);
+        }
     };
-    // the part of a work item that is prefetched one item ahead
-    struct Work {
-        int4 d0, d1, d2, d3, d4, d5; // ChunkUnit
-        int plane, first_reg, ipl, grel;
-    };
-    auto load_work = [&](uint32_t w, Work &k) {
-        const int unit_id = (int)(w / per_unit);
-        const uint32_t r  = w - (uint32_t)unit_id * per_unit;
-        k.ipl             = (int)(r / (uint32_t)a.g_count);
-        k.grel            = (int)(r - (uint32_t)k.ipl * (uint32_t)a.g_count);
-        const int4 *u     = reinterpret_cast<const int4 *>(a.units + unit_id);
-        k.d0 = u[0], k.d1 = u[1], k.d2 = u[2], k.d3 = u[3], k.d4 = u[4], k.d5 = u[5];
-        k.plane     = a.planes[k.ipl];
-        k.first_reg = a.plane_first_reg[k.plane];
-    };
-    auto ex_of = [&](const Work &k) -> const double * {
-        return a.cache + (((size_t)k.ipl * a.cache_groups + (a.g_begin + k.grel)) * a.list_pseg + k.d0.z) * P;
+    // level 2 (descriptor visible): angle weights and incoming boundary flux. Boundary values read here are
+    // never written by the same launch (a launch is one boundary phase / one Jacobi buffer).
+    auto prefetch_flux = [&](ChunkWork *k) {
+        if (wl == 0 && lane < 12) {
+            const int p = lane & 3, kind = lane >> 2;
+            if (p < P) {
+                const int g     = a.g_begin + k->grel;
+                const int plane = k->pinfo.x;
+                if (kind == 0)
+                    cp_async_8(&k->wt[p], a.wt_v_st + plane * a.n_ang + k->u.ang[p]);
+                else {
+                    const int slot = kind == 1 ? k->u.in_f[p] : k->u.in_b[p];
+                    cp_async_8(kind == 1 ? &k->cf[p] : &k->cb[p],
+                               a.bc_in + ((size_t)plane * a.bc_per_group + slot) * GP + g);
+                }
+            }
+        }
     };
     // TMA bulk copies of one (super-)block: FSR ids into buffer fi, attenuations into exb
-    auto issue_fsr = [&](int fi, const Work &k, int k_off, int n) {
-        if (lane == 0) {
+    auto issue_fsr = [&](int fi, const ChunkWork *k, int k_off, int n) {
+        if (leader) {
             const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar + fi, bytes);
-            bulk_g2s(fbuf + fi * caps, seg_fsr + k.d0.x + k_off, bytes, bar + fi);
+            bulk_g2s(fbuf + fi * caps, seg_fsr + k->u.seg_begin + k_off, bytes, bar + fi);
         }
     };
-    auto issue_ex = [&](const Work &k, int k_off, int n) {
-        if (lane == 0) {
+    auto issue_ex = [&](const ChunkWork *k, int k_off, int n) {
+        if (leader) {
+            const int g        = a.g_begin + k->grel;
+            const double *ex_g = a.cache + (((size_t)k->ipl * a.cache_groups + g) * a.list_pseg + k->u.cpos) * P;
             const uint32_t bytes = (uint32_t)((n + 3) & ~3) * (uint32_t)P * 8u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar + 2, bytes);
-            const char *src = reinterpret_cast<const char *>(ex_of(k) + (size_t)k_off * P);
+            const char *src = reinterpret_cast<const char *>(ex_g + (size_t)k_off * P);
             for (uint32_t off = 0; off < bytes; off += 16384u) // <= 16 KB per bulk copy
                 bulk_g2s(reinterpret_cast<char *>(exb) + off, src + off, min(16384u, bytes - off), bar + 2);
         }
     };
     // asynchronous striped q-bar gather (lanes on consecutive segments) straight into shared memory
-    auto gather_q = [&](int fi, const Work &k, int n) {
+    auto gather_q = [&](int fi, const ChunkWork *k, int n) {
         mbar_wait(bar + fi, (par_f >> fi) & 1u);
         par_f ^= 1u << fi;
-        const double *qf  = a.q + (size_t)k.grel * a.n_reg + k.first_reg;
+        const double *qf  = a.q + (size_t)k->grel * a.n_reg + k->pinfo.y;
         const int32_t *fb = fbuf + fi * caps;
-#pragma unroll 4
-        for (int i = lane; i < n; i += 32)
+#pragma unroll 8
+        for (int i = tl; i < n; i += T)
             cp_async_8(qb + i, qf + fb[i]);
     };
     auto wait_staged = [&]() {
         mbar_wait(bar + 2, par_e);
         par_e ^= 1u;
         cp_async_wait_all();
-        __syncwarp();
+        team_sync();
     };
-    auto reduce_tally = [&](int fi, const Work &k, int n) {
-        double *tf        = a.tally + (size_t)k.grel * a.n_reg + k.first_reg;
+    auto reduce_tally = [&](int fi, const ChunkWork *k, int n) {
+        double *tf        = a.tally + (size_t)k->grel * a.n_reg + k->pinfo.y;
         const int32_t *fb = fbuf + fi * caps;
-#pragma unroll 4
-        for (int i = lane; i < n; i += 32)
+#pragma unroll 8
+        for (int i = tl; i < n; i += T)
             atomicAdd(&tf[fb[i]], ab[i]);
     };
+    // One staged (super-)block. cf: forward flux entering the block (team-uniform), eb: backward flux entering
+    // it from the far side. Leaves the contributions in ab; returns the forward flux leaving the block
+    // (valid in the last lane of the team) and the backward flux leaving it (valid in team lane 0).
+    auto block = [&](int n, const double (&wt)[P], const double (&cf)[P], const double (&eb)[P], double (&out_fwd)[P],
+                     double (&out_bwd)[P]) {
+        const int L  = ((n + T - 1) / T) | 1;
+        const int lo = min(tl * L, n), hi = min(lo + L, n);
+        double A[P], Af[P], Bf[P], Ab[P], Bb[P];
+        chunk_compose<P>(exb, qb, lo, hi, A, Bf, Bb);
+        chunk_scan<P>(lane, A, Af, Bf, Ab, Bb);
+        double cfw[P], ebw[P];
+#pragma unroll
+        for (int p = 0; p < P; p++)
+            cfw[p] = cf[p], ebw[p] = eb[p];
+        if (NW > 1) { // maps of the other warps of the team: forward through the lower, backward through the higher ones
+            if (lane == 31) {
+#pragma unroll
+                for (int p = 0; p < P; p++)
+                    s_tot[team][wl][p][0] = Af[p], s_tot[team][wl][p][1] = Bf[p];
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int p = 0; p < P; p++)
+                    s_tot[team][wl][p][2] = Ab[p], s_tot[team][wl][p][3] = Bb[p];
+            }
+            team_sync();
+#pragma unroll
+            for (int w = 0; w < NW - 1; w++) {
+                if (w < wl) {
+#pragma unroll
+                    for (int p = 0; p < P; p++)
+                        cfw[p] = fma(s_tot[team][w][p][0], cfw[p], s_tot[team][w][p][1]);
+                }
+            }
+#pragma unroll
+            for (int w = NW - 1; w > 0; w--) {
+                if (w > wl) {
+#pragma unroll
+                    for (int p = 0; p < P; p++)
+                        ebw[p] = fma(s_tot[team][w][p][2], ebw[p], s_tot[team][w][p][3]);
+                }
+            }
+        }
+        double psi_f[P], psi_b[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const double of = fma(Af[p], cfw[p], Bf[p]); // flux leaving this lane's chunk, forward
+            const double ob = fma(Ab[p], ebw[p], Bb[p]); // ... backward
+            const double in_f = __shfl_up_sync(0xffffffffu, of, 1);
+            const double in_b = __shfl_down_sync(0xffffffffu, ob, 1);
+            psi_f[p]   = lane == 0 ? cfw[p] : in_f;
+            psi_b[p]   = lane == 31 ? ebw[p] : in_b;
+            out_fwd[p] = of;
+        }
+        chunk_walk<P>(exb, qb, ab, lo, hi, wt, psi_f, psi_b);
+#pragma unroll
+        for (int p = 0; p < P; p++)
+            out_bwd[p] = psi_b[p];
+    };
 
-    // ---- software pipeline over the work items: counter two ahead, descriptor one ahead ----
-    uint32_t w_cur = next_work();
-    uint32_t w_nxt = next_work();
-    Work cur, nxt;
-    if (w_cur < total)
-        load_work(w_cur, cur);
+    // ---- software pipeline over the work items: counter two ahead, descriptor and boundary flux one ahead ----
+    // plain PTX atomic: the compiler's warp-aggregated atomicAdd would broadcast (and so wait for) the result at once
+    auto fetch = [&]() -> uint32_t {
+        uint32_t w = 0u;
+        if (leader)
+            asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(w) : "l"(a.counter) : "memory");
+        return w;
+    };
+    uint32_t share_slot = 0u;
+    auto share = [&](uint32_t w) -> uint32_t { // leader's value to the whole team (one barrier; alternating slots)
+        if (NW == 1)
+            return __shfl_sync(0xffffffffu, w, 0);
+        if (leader)
+            s_w[2 * team + share_slot] = w;
+        team_sync();
+        const uint32_t r = s_w[2 * team + share_slot];
+        share_slot ^= 1u;
+        return r;
+    };
+    uint32_t w_cur = share(fetch());
+    uint32_t w_nxt = share(fetch());
+    int cs = 0; // slot of `cur` in s_work[team]
+    if (w_cur < total) {
+        prefetch_unit(w_cur, &s_work[team][cs]);
+        cp_async_wait_all();
+        team_sync();
+        prefetch_flux(&s_work[team][cs]);
+        cp_async_wait_all();
+        team_sync();
+    }
     bool staged = false; // attenuations + q-bar of `cur` already on their way (issued by the previous item)
     int fi      = 0;     // FSR-id buffer of `cur`
 
     while (w_cur < total) {
-        const uint32_t w_nn = next_work();
-        if (w_nxt < total)
-            load_work(w_nxt, nxt);
+        const uint32_t w_nn_raw = fetch(); // consumed at the end of this item
+        const ChunkWork *cur = &s_work[team][cs];
+        ChunkWork *nxt       = &s_work[team][cs ^ 1];
+        const bool have_nxt  = w_nxt < total;
+        if (have_nxt)
+            prefetch_unit(w_nxt, nxt);
 
-        const int nseg = cur.d0.y;
-        const int g    = a.g_begin + cur.grel;
-        const int ang[4]   = {cur.d1.x, cur.d1.y, cur.d1.z, cur.d1.w};
-        const int in_f[4]  = {cur.d2.x, cur.d2.y, cur.d2.z, cur.d2.w};
-        const int in_b[4]  = {cur.d3.x, cur.d3.y, cur.d3.z, cur.d3.w};
-        const int out_f[4] = {cur.d4.x, cur.d4.y, cur.d4.z, cur.d4.w};
-        const int out_b[4] = {cur.d5.x, cur.d5.y, cur.d5.z, cur.d5.w};
-        double wt[P], cf[P], cb[P];
-        const double *bc_in_pl = a.bc_in + (size_t)cur.plane * a.bc_per_group * GP;
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-            wt[p] = a.wt_v_st[cur.plane * a.n_ang + ang[p]];
-            cf[p] = bc_in_pl[(size_t)in_f[p] * GP + g];
-            cb[p] = bc_in_pl[(size_t)in_b[p] * GP + g];
-        }
+        const int nseg = cur->u.nseg;
+        double cf_out[P], cb_out[P];
 
         if (nseg <= caps) {
             // ================= the whole track fits: one staged block, next item prefetched =================
@@ -389,21 +473,21 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
                 issue_ex(cur, 0, nseg);
                 gather_q(fi, cur, nseg);
             }
-            const bool pre = w_nxt < total && nxt.d0.y <= caps;
+            wait_staged(); // also: the next item's descriptor and this item's boundary flux have landed
+            const bool pre = have_nxt && nxt->u.nseg <= caps;
             if (pre)
-                issue_fsr(fi ^ 1, nxt, 0, nxt.d0.y);
-            wait_staged();
-            const int L  = ((nseg + 31) >> 5) | 1;
-            const int lo = min(lane * L, nseg), hi = min(lo + L, nseg);
-            double psi_b[P];
-            chunk_block<P>(exb, qb, ab, lane, lo, hi, wt, cf, cb, psi_b);
+                issue_fsr(fi ^ 1, nxt, 0, nxt->u.nseg);
+            if (have_nxt)
+                prefetch_flux(nxt);
+            double wt[P], cf[P], cb[P];
 #pragma unroll
             for (int p = 0; p < P; p++)
-                cb[p] = psi_b[p]; // lane 0: backward flux leaving the ray
-            __syncwarp();
+                wt[p] = cur->wt[p], cf[p] = cur->cf[p], cb[p] = cur->cb[p];
+            block(nseg, wt, cf, cb, cf_out, cb_out);
+            team_sync();
             if (pre) { // exb and qb are free again: stage the next track behind this one's reductions
-                issue_ex(nxt, 0, nxt.d0.y);
-                gather_q(fi ^ 1, nxt, nxt.d0.y);
+                issue_ex(nxt, 0, nxt->u.nseg);
+                gather_q(fi ^ 1, nxt, nxt->u.nseg);
             }
             reduce_tally(fi, cur, nseg);
             staged = pre;
@@ -411,22 +495,30 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
                 fi ^= 1;
         } else {
             // ================= long track: super-blocks of caps segments chained by a carried flux =================
+            cp_async_wait_all();
+            team_sync();
+            if (have_nxt)
+                prefetch_flux(nxt);
             const int nsb = (nseg + caps - 1) / caps;
+            double wt[P], cb[P], cf[P];
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                wt[p] = cur->wt[p], cf[p] = cur->cf[p], cb[p] = cur->cb[p];
             for (int sb = nsb - 1; sb >= 1; --sb) { // pass A: backward flux entering each super-block
                 const int n = min(caps, nseg - sb * caps);
                 issue_fsr(fi, cur, sb * caps, n);
                 issue_ex(cur, sb * caps, n);
                 gather_q(fi, cur, n);
                 wait_staged();
-                const int L  = ((n + 31) >> 5) | 1;
-                const int lo = min(lane * L, n), hi = min(lo + L, n);
-                if (lane == 0) {
+                const int L  = ((n + T - 1) / T) | 1;
+                const int lo = min(tl * L, n), hi = min(lo + L, n);
+                if (leader) {
 #pragma unroll
                     for (int p = 0; p < P; p++)
                         sc[sb * P + p] = cb[p];
                 }
-                double A[P], B[P];
-                chunk_compose_bwd<P>(exb, qb, lo, hi, A, B);
+                double A[P], Bf[P], B[P];
+                chunk_compose<P>(exb, qb, lo, hi, A, Bf, B);
 #pragma unroll
                 for (int s = 1; s < 32; s <<= 1) { // ordered butterfly: total = L_0 o L_1 o ... o L_31
 #pragma unroll
@@ -440,10 +532,25 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
                         A[p] *= Ao;
                     }
                 }
+                if (NW > 1) {
+                    if (lane == 0) {
 #pragma unroll
-                for (int p = 0; p < P; p++)
-                    cb[p] = fma(A[p], cb[p], B[p]);
-                __syncwarp();
+                        for (int p = 0; p < P; p++)
+                            s_tot[team][wl][p][2] = A[p], s_tot[team][wl][p][3] = B[p];
+                    }
+                    team_sync();
+#pragma unroll
+                    for (int w = NW - 1; w >= 0; w--) {
+#pragma unroll
+                        for (int p = 0; p < P; p++)
+                            cb[p] = fma(s_tot[team][w][p][2], cb[p], s_tot[team][w][p][3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int p = 0; p < P; p++)
+                        cb[p] = fma(A[p], cb[p], B[p]);
+                }
+                team_sync();
             }
             for (int sb = 0; sb < nsb; ++sb) { // pass B: forward chain, both walks, tally
                 const int n = min(caps, nseg - sb * caps);
@@ -451,39 +558,62 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
                 issue_ex(cur, sb * caps, n);
                 gather_q(fi, cur, n);
                 wait_staged();
-                const int L  = ((n + 31) >> 5) | 1;
-                const int lo = min(lane * L, n), hi = min(lo + L, n);
-                double eb[P], psi_b[P];
+                double eb[P], of[P], ob[P];
 #pragma unroll
                 for (int p = 0; p < P; p++)
                     eb[p] = sb > 0 ? sc[sb * P + p] : cb[p];
-                chunk_block<P>(exb, qb, ab, lane, lo, hi, wt, cf, eb, psi_b);
-                if (sb == 0) {
+                block(n, wt, cf, eb, of, ob);
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    if (NW > 1) { // the last lane of the team holds the flux leaving the block
+                        if (tl == T - 1)
+                            s_tot[team][0][p][0] = of[p];
+                    } else {
+                        cf[p] = __shfl_sync(0xffffffffu, of[p], 31);
+                    }
+                    if (sb == 0)
+                        cb_out[p] = ob[p];
+                }
+                team_sync();
+                if (NW > 1) {
 #pragma unroll
                     for (int p = 0; p < P; p++)
-                        cb[p] = psi_b[p];
+                        cf[p] = s_tot[team][0][p][0];
                 }
-                __syncwarp();
                 reduce_tally(fi, cur, n);
-                __syncwarp();
+                team_sync();
             }
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                cf_out[p] = cf[p];
             staged = false;
         }
 
-        // ---- outgoing boundary flux, written where BoundaryCondition::update would copy it ----
-        if (lane == 0) {
-            double *bc_out_pl = a.bc_out + (size_t)cur.plane * a.bc_per_group * GP;
+        // ---- outgoing boundary flux, written where BoundaryCondition::update would copy it: the forward
+        //      exit flux by the last lane of the team, the backward exit flux by its first lane ----
+        if (tl == T - 1 || leader) {
+            const int g       = a.g_begin + cur->grel;
+            double *bc_out_pl = a.bc_out + (size_t)cur->pinfo.x * a.bc_per_group * GP + g;
+            if (tl == T - 1) {
 #pragma unroll
-            for (int p = 0; p < P; p++) {
-                if (out_f[p] != INT32_MIN)
-                    bc_out_pl[(size_t)(out_f[p] >= 0 ? out_f[p] : -(out_f[p] + 1)) * GP + g] = out_f[p] >= 0 ? cf[p] : 0.0;
-                if (out_b[p] != INT32_MIN)
-                    bc_out_pl[(size_t)(out_b[p] >= 0 ? out_b[p] : -(out_b[p] + 1)) * GP + g] = out_b[p] >= 0 ? cb[p] : 0.0;
+                for (int p = 0; p < P; p++) {
+                    const int o = cur->u.out_f[p];
+                    if (o != INT32_MIN)
+                        bc_out_pl[(size_t)(o >= 0 ? o : -(o + 1)) * GP] = o >= 0 ? cf_out[p] : 0.0;
+                }
+            }
+            if (leader) {
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    const int o = cur->u.out_b[p];
+                    if (o != INT32_MIN)
+                        bc_out_pl[(size_t)(o >= 0 ? o : -(o + 1)) * GP] = o >= 0 ? cb_out[p] : 0.0;
+                }
             }
         }
-        __syncwarp();
+        const uint32_t w_nn = share(w_nn_raw); // also fences the team before buffers and slots are reused
         w_cur = w_nxt, w_nxt = w_nn;
-        cur = nxt;
+        cs ^= 1;
     }
 }
 

@@ -83,11 +83,13 @@ def test_sweep1g_matches_reference_golden(case, max_polar, kernel):
 
 @pytest.mark.parametrize("case", ["mini2d_gs", "mini2d_jacobi", "mini3d_gs", "3x3_s05_gs"])
 @pytest.mark.parametrize("max_polar", [1, 2, 3])
-def test_chunk_kernel_superblocks_match_reference_golden(case, max_polar):
-    """CHUNK kernel with a 32-segment staging cap: every longer track is chained through super-blocks."""
+@pytest.mark.parametrize("chunk_cap", [32, -64, -100000])
+def test_chunk_kernel_superblocks_match_reference_golden(case, max_polar, chunk_cap):
+    """CHUNK kernel with a small staging cap: every longer track is chained through super-blocks
+    (negative cap: two warps per track, with and without super-blocks)."""
     flat, gold = load_case(case)
     gs = bool(gold["gs_boundary"][0])
-    sw = _sweeper(flat, boundary_update=0 if gs else 1, max_polar=max_polar, kernel=4, chunk_cap=32)
+    sw = _sweeper(flat, boundary_update=0 if gs else 1, max_polar=max_polar, kernel=4, chunk_cap=chunk_cap)
     n = 0
     for rec in records(gold):
         if int(rec["mode"][0]) != 0:
