@@ -38,6 +38,7 @@ struct TrackList { // one launch of the track kernel: units of one (unique plane
     int32_t max_nseg   = 0; // longest track of the list
     ChunkUnit *d_cunits = nullptr; // self-contained descriptors of the same units (chunk kernel)
     int2 *d_pinfo       = nullptr; // per plane of the list: {macroplane, first FSR}
+    int4 *d_len_begin   = nullptr; // per unit and polar angle: start of that angle's own segment lengths
     double *d_cache    = nullptr; // attenuation cache of this list (CACHED kernel)
 };
 
@@ -68,7 +69,8 @@ struct mocb200_sweeper {
     double *d_seg_len = nullptr;
     int32_t *d_seg_fsr = nullptr;
     Cross *d_cross     = nullptr;
-    Bundle *d_bundles  = nullptr;
+    Bundle *d_bundles  = nullptr; // strict bundles (item kernel)
+    Bundle *d_tbundles = nullptr; // bundles of the track lists (topological when the attenuation cache is used)
     double *d_rsin = nullptr, *d_wt = nullptr, *d_curw = nullptr, *d_flxw = nullptr;
     int32_t *d_bc_offset = nullptr, *d_bc_size_x = nullptr, *d_bc_dst_off = nullptr, *d_bc_dst_kind = nullptr;
     int32_t *d_plane_first_reg = nullptr, *d_plane_surf_offset = nullptr;
@@ -260,32 +262,100 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     h->reg_lo = p.plane_first_reg[h->plane_begin];
     h->reg_hi = (h->plane_end < p.n_plane) ? p.plane_first_reg[h->plane_end] : p.n_reg;
 
-    // ---- polar bundles: angles of one octant that share a geometry ----
-    std::vector<Bundle> bundles;
-    std::vector<int> bundle_phase, bundle_geom;
-    for (int oct = 0; oct < 2; oct++) {
-        for (int geom = 0; geom < p.n_geom; geom++) {
-            std::vector<int> angs;
-            for (int a = oct * p.ndir_oct; a < (oct + 1) * p.ndir_oct; a++)
-                if (p.ang_geom[a] == geom)
-                    angs.push_back(a);
-            if (angs.empty())
-                continue;
-            int nchunk = ((int)angs.size() + max_polar - 1) / max_polar;
-            for (int c = 0; c < nchunk; c++) {
-                int lo = (int)((int64_t)angs.size() * c / nchunk), hi = (int)((int64_t)angs.size() * (c + 1) / nchunk);
-                Bundle b{};
-                b.np = hi - lo;
-                for (int i = lo; i < hi; i++)
-                    b.ang[i - lo] = angs[i];
-                for (int i = b.np; i < kMaxPolar; i++)
-                    b.ang[i] = angs[lo];
-                bundles.push_back(b);
-                bundle_phase.push_back(oct);
-                bundle_geom.push_back(geom);
+    // ---- kernel selection: the attenuation cache needs 8 bytes per (padded segment, polar angle, group, plane) ----
+    h->kernel = opt.kernel;
+    if (h->kernel < MOCB200_KERNEL_AUTO || h->kernel > MOCB200_KERNEL_CHUNK)
+        return fail(h, MOCB200_ERR_INVALID, "unknown kernel selection %d", h->kernel);
+    if (h->kernel == MOCB200_KERNEL_AUTO || h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK) {
+        int64_t bytes = 0;
+        for (int u = 0; u < p.n_unique; u++) {
+            int64_t n_planes_u = 0;
+            for (int ip = h->plane_begin; ip < h->plane_end; ip++)
+                n_planes_u += p.plane_unique[ip] == u;
+            for (int a = 0; a < p.n_ang && n_planes_u; a++) {
+                const size_t gi = (size_t)u * p.n_geom + p.ang_geom[a];
+                for (int64_t t = p.geom_trk_begin[gi]; t < p.geom_trk_begin[gi + 1]; t++)
+                    bytes += ((p.trk_seg_begin[t + 1] - p.trk_seg_begin[t] + 3) & ~(int64_t)3) * n_planes_u * h->GP * 8;
             }
         }
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
+        const bool fits = (double)bytes < 0.7 * (double)free_b;
+        if (!fits && h->kernel != MOCB200_KERNEL_AUTO)
+            return fail(h, MOCB200_ERR_INVALID, "attenuation cache (%lld MiB) does not fit in device memory",
+                        (long long)(bytes >> 20));
+        h->kernel = !fits ? MOCB200_KERNEL_TRACK
+                          : (h->kernel == MOCB200_KERNEL_CACHED ? MOCB200_KERNEL_CACHED : MOCB200_KERNEL_CHUNK);
     }
+    const bool cached_build = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK;
+
+    // ---- topology classes of the geometry classes ----
+    // The reference keeps one ray set per (azimuth, polar) angle; polar copies of an azimuth visit the same
+    // FSRs, boundary slots and coarse surfaces but may differ in the last bits of their segment lengths
+    // (per-angle volume correction, ray_data.cpp). Kernels that read the attenuation CACHE never read lengths
+    // (the cache is built per polar angle from that angle's own lengths), so for them polar copies are
+    // bundled whenever the topology matches; kernels that read lengths need bit-identical rays.
+    std::vector<int> topo_of(p.n_geom);
+    for (int g = 0; g < p.n_geom; g++) {
+        topo_of[g] = g;
+        for (int g2 = 0; g2 < g && cached_build && topo_of[g] == g; g2++) {
+            if (topo_of[g2] != g2)
+                continue;
+            bool same = true;
+            for (int u = 0; u < p.n_unique && same; u++) {
+                const int64_t a0 = p.geom_trk_begin[(size_t)u * p.n_geom + g], a1 = p.geom_trk_begin[(size_t)u * p.n_geom + g + 1];
+                const int64_t b0 = p.geom_trk_begin[(size_t)u * p.n_geom + g2], b1 = p.geom_trk_begin[(size_t)u * p.n_geom + g2 + 1];
+                same = (a1 - a0) == (b1 - b0);
+                for (int64_t i = 0; i < a1 - a0 && same; i++) {
+                    const int64_t ta = a0 + i, tb = b0 + i;
+                    const int64_t na = p.trk_seg_begin[ta + 1] - p.trk_seg_begin[ta];
+                    const int64_t nc = p.trk_cm_begin[ta + 1] - p.trk_cm_begin[ta];
+                    same = na == p.trk_seg_begin[tb + 1] - p.trk_seg_begin[tb] &&
+                           nc == p.trk_cm_begin[tb + 1] - p.trk_cm_begin[tb] &&
+                           std::equal(p.trk_bc + 2 * ta, p.trk_bc + 2 * ta + 2, p.trk_bc + 2 * tb) &&
+                           std::equal(p.trk_cm_start + 4 * ta, p.trk_cm_start + 4 * ta + 4, p.trk_cm_start + 4 * tb) &&
+                           std::equal(p.seg_fsr + p.trk_seg_begin[ta], p.seg_fsr + p.trk_seg_begin[ta] + na,
+                                      p.seg_fsr + p.trk_seg_begin[tb]) &&
+                           std::equal(p.cm_data + p.trk_cm_begin[ta], p.cm_data + p.trk_cm_begin[ta] + nc,
+                                      p.cm_data + p.trk_cm_begin[tb]);
+                }
+            }
+            if (same)
+                topo_of[g] = g2;
+        }
+    }
+
+    // ---- polar bundles: angles of one octant that share a geometry (strict: bit-identical rays, for the
+    //      kernels that read lengths; topological: for the kernels on the attenuation cache) ----
+    std::vector<Bundle> bundles, tbundles;
+    std::vector<int> bundle_phase, bundle_geom, tbundle_phase, tbundle_geom;
+    auto make_bundles = [&](bool topo, std::vector<Bundle> &out, std::vector<int> &out_phase, std::vector<int> &out_geom) {
+        for (int oct = 0; oct < 2; oct++) {
+            for (int geom = 0; geom < p.n_geom; geom++) {
+                std::vector<int> angs;
+                for (int a = oct * p.ndir_oct; a < (oct + 1) * p.ndir_oct; a++)
+                    if ((topo ? topo_of[p.ang_geom[a]] : p.ang_geom[a]) == geom)
+                        angs.push_back(a);
+                if (angs.empty())
+                    continue;
+                int nchunk = ((int)angs.size() + max_polar - 1) / max_polar;
+                for (int c = 0; c < nchunk; c++) {
+                    int lo = (int)((int64_t)angs.size() * c / nchunk), hi = (int)((int64_t)angs.size() * (c + 1) / nchunk);
+                    Bundle b{};
+                    b.np = hi - lo;
+                    for (int i = lo; i < hi; i++)
+                        b.ang[i - lo] = angs[i];
+                    for (int i = b.np; i < kMaxPolar; i++)
+                        b.ang[i] = angs[lo];
+                    out.push_back(b);
+                    out_phase.push_back(oct);
+                    out_geom.push_back(geom);
+                }
+            }
+        }
+    };
+    make_bundles(false, bundles, bundle_phase, bundle_geom);
+    make_bundles(true, tbundles, tbundle_phase, tbundle_geom);
 
     // ---- crossing lists, one pair per track ----
     std::vector<Cross> cross;
@@ -366,9 +436,6 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     h->stats.unique_segments    = p.n_seg;
 
     // ---- track kernel: padded geometry, crossing lists with sentinels, per-4-segment crossing pointers ----
-    h->kernel = opt.kernel;
-    if (h->kernel < MOCB200_KERNEL_AUTO || h->kernel > MOCB200_KERNEL_CHUNK)
-        return fail(h, MOCB200_ERR_INVALID, "unknown kernel selection %d", h->kernel);
     {
         std::vector<int64_t> pbegin(p.n_trk + 1, 0);
         for (int64_t t = 0; t < p.n_trk; t++) {
@@ -434,25 +501,41 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                 continue;
             for (int phase = 0; phase < (jacobi ? 1 : 2); phase++) {
                 for (int np = 1; np <= kMaxPolar; np++) {
-                    std::vector<TrackUnit> units;
-                    for (size_t b = 0; b < bundles.size(); b++) {
-                        if (bundles[b].np != np || (!jacobi && bundle_phase[b] != phase))
+                    struct UnitRec {
+                        TrackUnit tu;
+                        int4 len_begin; // per polar angle: where that angle's own segment lengths start
+                    };
+                    std::vector<UnitRec> recs;
+                    for (size_t b = 0; b < tbundles.size(); b++) {
+                        if (tbundles[b].np != np || (!jacobi && tbundle_phase[b] != phase))
                             continue;
-                        int64_t t0 = p.geom_trk_begin[(size_t)u * p.n_geom + bundle_geom[b]];
-                        int64_t t1 = p.geom_trk_begin[(size_t)u * p.n_geom + bundle_geom[b] + 1];
+                        int64_t t0 = p.geom_trk_begin[(size_t)u * p.n_geom + tbundle_geom[b]];
+                        int64_t t1 = p.geom_trk_begin[(size_t)u * p.n_geom + tbundle_geom[b] + 1];
                         for (int64_t t = t0; t < t1; t++) {
-                            TrackUnit tu{};
-                            tu.seg_begin = (int32_t)pbegin[t];
-                            tu.nseg      = (int32_t)(p.trk_seg_begin[t + 1] - p.trk_seg_begin[t]);
-                            tu.bc0 = p.trk_bc[2 * t], tu.bc1 = p.trk_bc[2 * t + 1];
-                            tu.bundle = (int32_t)b;
-                            units.push_back(tu);
+                            UnitRec r{};
+                            r.tu.seg_begin = (int32_t)pbegin[t];
+                            r.tu.nseg      = (int32_t)(p.trk_seg_begin[t + 1] - p.trk_seg_begin[t]);
+                            r.tu.bc0 = p.trk_bc[2 * t], r.tu.bc1 = p.trk_bc[2 * t + 1];
+                            r.tu.bundle = (int32_t)b;
+                            int32_t lb[kMaxPolar];
+                            for (int q = 0; q < kMaxPolar; q++) {
+                                const int gq = p.ang_geom[tbundles[b].ang[q]];
+                                lb[q] = (int32_t)pbegin[p.geom_trk_begin[(size_t)u * p.n_geom + gq] + (t - t0)];
+                            }
+                            r.len_begin = make_int4(lb[0], lb[1], lb[2], lb[3]);
+                            recs.push_back(r);
                         }
                     }
-                    if (units.empty())
+                    if (recs.empty())
                         continue;
-                    std::stable_sort(units.begin(), units.end(),
-                                     [](const TrackUnit &x, const TrackUnit &y) { return x.nseg > y.nseg; });
+                    std::stable_sort(recs.begin(), recs.end(),
+                                     [](const UnitRec &x, const UnitRec &y) { return x.tu.nseg > y.tu.nseg; });
+                    std::vector<TrackUnit> units;
+                    std::vector<int4> len_begin;
+                    for (const auto &r : recs) {
+                        units.push_back(r.tu);
+                        len_begin.push_back(r.len_begin);
+                    }
                     TrackList tl;
                     for (auto &tu : units) {
                         tu.cpos = (int32_t)tl.pseg;
@@ -468,7 +551,8 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                     tl.segs = segs * np * tl.n_planes;
                     if ((int64_t)tl.n_units * tl.n_planes * p.n_group >= (int64_t)UINT32_MAX - 64)
                         return fail(h, MOCB200_ERR_INVALID, "track list too large for 32-bit scheduling");
-                    if ((rc2 = dev_upload(h, &tl.d_units, units)) || (rc2 = dev_upload(h, &tl.d_planes, planes)))
+                    if ((rc2 = dev_upload(h, &tl.d_units, units)) || (rc2 = dev_upload(h, &tl.d_planes, planes)) ||
+                        (rc2 = dev_upload(h, &tl.d_len_begin, len_begin)))
                         return rc2;
                     {
                         // chunk-kernel descriptors: boundary linkage resolved once (boundary_condition.cpp:155-191)
@@ -478,7 +562,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                             ChunkUnit &c = cu[i];
                             c.seg_begin = tu.seg_begin, c.nseg = tu.nseg, c.cpos = tu.cpos, c.pad = 0;
                             for (int q = 0; q < kMaxPolar; q++) {
-                                const int ang = bundles[tu.bundle].ang[q];
+                                const int ang = tbundles[tu.bundle].ang[q];
                                 c.ang[q]  = ang;
                                 c.in_f[q] = p.bc_offset[ang] + tu.bc0;
                                 c.in_b[q] = p.bc_offset[ang + p.n_ang] + tu.bc1;
@@ -605,7 +689,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     UP(h->d_seg_fsr, p.seg_fsr, p.n_seg);
     if ((rc = dev_upload(h, &h->d_cross, cross)))
         return rc;
-    if ((rc = dev_upload(h, &h->d_bundles, bundles)))
+    if ((rc = dev_upload(h, &h->d_bundles, bundles)) || (rc = dev_upload(h, &h->d_tbundles, tbundles)))
         return rc;
     UP(h->d_rsin, p.ang_rsintheta, p.n_ang);
     UP(h->d_wt, p.wt_v_st, (size_t)p.n_plane * p.n_ang);
@@ -669,19 +753,6 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     h->cache_valid.assign(p.n_group, false);
     if ((rc = dev_alloc(h, &h->d_qg, (size_t)p.n_group * p.n_reg)) || (rc = dev_alloc(h, &h->d_tg, (size_t)p.n_group * p.n_reg)))
         return rc;
-    if (h->kernel == MOCB200_KERNEL_AUTO || h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK) {
-        // the attenuation cache: 8 bytes per (padded segment, polar angle, group, plane)
-        int64_t bytes = 0;
-        for (const auto &tl : h->tlists)
-            bytes += tl.pseg * tl.np * tl.n_planes * (int64_t)h->GP * 8;
-        size_t free_b = 0, total_b = 0;
-        CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
-        const bool fits = (double)bytes < 0.8 * (double)free_b;
-        if (!fits && h->kernel != MOCB200_KERNEL_AUTO)
-            return fail(h, MOCB200_ERR_INVALID, "attenuation cache (%lld MiB) does not fit in device memory",
-                        (long long)(bytes >> 20));
-        h->kernel = !fits ? MOCB200_KERNEL_TRACK : (h->kernel == MOCB200_KERNEL_CACHED ? MOCB200_KERNEL_CACHED : MOCB200_KERNEL_CHUNK);
-    }
     h->stats.device_bytes = h->device_bytes;
     return MOCB200_OK;
 }
@@ -1085,7 +1156,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         if (dirty) {
             for (const auto &tl : h->tlists) {
                 CacheArgs c{};
-                c.units = tl.d_units, c.n_units = tl.n_units, c.bundles = h->d_bundles;
+                c.units = tl.d_units, c.n_units = tl.n_units, c.bundles = h->d_tbundles, c.len_begin = tl.d_len_begin;
                 c.planes = tl.d_planes, c.n_planes = tl.n_planes;
                 c.seg_len = h->d_pseg_len, c.seg_fsr = h->d_pseg_fsr, c.ang_rsintheta = h->d_rsin;
                 c.plane_first_reg = h->d_plane_first_reg, c.xstr = h->d_xstr;
@@ -1202,7 +1273,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 uint32_t *counter   = h->d_counters + h->lists.size() + il;
                 WarpArgs a{};
                 a.units = tl.d_units, a.n_units = tl.n_units, a.counter = counter;
-                a.bundles = h->d_bundles, a.planes = tl.d_planes, a.n_planes = tl.n_planes;
+                a.bundles = h->d_tbundles, a.planes = tl.d_planes, a.n_planes = tl.n_planes;
                 a.seg_len = h->d_pseg_len, a.seg_fsr = h->d_pseg_fsr, a.xptr = h->d_xptr, a.cross = h->d_xcross;
                 a.ang_rsintheta = h->d_rsin, a.wt_v_st = h->d_wt, a.cur_w = h->d_curw, a.flx_w = h->d_flxw;
                 a.bc_offset = h->d_bc_offset, a.bc_size_x = h->d_bc_size_x;

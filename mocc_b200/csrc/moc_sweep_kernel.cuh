@@ -662,6 +662,7 @@ struct CacheArgs {
     int32_t n_planes;
     const double *seg_len;
     const int32_t *seg_fsr;
+    const int4 *len_begin; // per unit and polar angle: start of that angle's own (padded) segment lengths
     const double *ang_rsintheta;
     const int32_t *plane_first_reg;
     const double *xstr; // [n_reg][GP]
@@ -692,15 +693,18 @@ __global__ void __launch_bounds__(512, 1) exp_cache_kernel(const CacheArgs a)
         const int plane     = a.planes[ipl];
         const int first_reg = a.plane_first_reg[plane];
         const TrackUnit u   = a.units[unit_id];
+        const int4 lb4      = a.len_begin[unit_id];
+        const int lb[4]     = {lb4.x, lb4.y, lb4.z, lb4.w};
         const int npad      = (u.nseg + 3) & ~3;
         for (int k = lane; k < npad; k += 32) {
             const bool valid = k < u.nseg;
-            const double len = a.seg_len[u.seg_begin + k];
             const int reg    = a.seg_fsr[u.seg_begin + k] + first_reg;
             for (int gi = 0; gi < a.g_count; gi++) {
-                const int g    = a.g_begin + gi;
-                const double t = a.xstr[(size_t)reg * a.GP + g] * len;
+                const int g     = a.g_begin + gi;
+                const double xs = a.xstr[(size_t)reg * a.GP + g];
                 for (int p = 0; p < P; p++) {
+                    // every polar angle has its own lengths (polar copies may differ in the last bits)
+                    const double t   = xs * a.seg_len[lb[p] + k];
                     const double nrs = -a.ang_rsintheta[a.bundles[u.bundle].ang[p]];
                     const double ex  = valid ? exp_interp(s_tab, t * nrs, c0, rspace) : 1.0;
                     size_t o;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of tuning knobs on the bench (kernel 4)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_sweep.py -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 for nw in 1 2; do
   MOCB200_CHUNK_NW=$nw timeout 300 python bench.py --steps 5 --warmup 3 --kernel 4 --no-cpu-baseline > gpurun_out/bench_nw$nw.json 2>gpurun_out/bench_nw$nw.err
   python - <<PY
