@@ -320,6 +320,12 @@ def main():
                              f"last inner): {r['updates']:.3e} updates in {r['seconds']:.2f} s, reference MoCSweeper "
                              f"(OpenMP, unmodified sources in oracle/_ref)"}
 
+    st = sw.stats()
+    kname = {1: "item", 2: "track", 3: "cached", 4: "chunk"}.get(int(st["kernel"]), "?")
+    if args.mode == "batched" and kname == "chunk":
+        kname = "cached"  # group-batched sweeps run the 8-group-lane warp kernel on the same cache
+    kfunc = {"item": "sweep_kernel", "track": "sweep_warp_kernel<CACHED=false>", "cached": "sweep_warp_kernel<CACHED=true>",
+             "chunk": "sweep_chunk_kernel"}[kname]
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -333,13 +339,14 @@ def main():
                        "mode": args.mode, "boundary_update": args.boundary, "segments": S, "resident_segments": n_useg,
                        "n_reg": n_reg, "groups": G, "n_inner": n_inner, "updates_per_step": updates_step,
                        "l2": "256 MB flush write between timed steps; device-resident inputs 450 MB > 126 MB L2",
-                       "kernel": "track" if args.kernel == 0 else "item"},
+                       "kernel": kname, "bundled_segments": int(st["swept_segments"])},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(ln.item()),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_track_kernel",
-                         "launch": f"the track-kernel launches of one inner sweep of {groups_per_call} group(s)",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": kfunc,
+                         "launch": f"the sweep-kernel launches of one inner sweep of {groups_per_call} group(s) "
+                                   f"(two boundary phases), averaged over the {n_inner} inners of every sweep call",
                          "ms_per_launch": sweep_ms, "updates_per_launch": upd_per_sweep,
                          "algorithmic_bytes_per_launch": bytes_contract,
                          "resident_layout_bytes_per_launch": bytes_resident,

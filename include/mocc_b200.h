@@ -233,6 +233,8 @@ typedef struct mocb200_stats {
     int64_t unique_segments;   /* segments resident on the device */
     int64_t device_bytes;      /* device memory held */
     int64_t items[2];          /* work items (track, direction) per boundary phase */
+    int64_t kernel;            /* MOCB200_KERNEL_* in use (AUTO resolved) */
+    int64_t swept_segments;    /* segments the track lists hold per plane set (polar copies bundled) */
 } mocb200_stats;
 int mocb200_get_stats(const mocb200_sweeper *h, mocb200_stats *out);
 

@@ -64,7 +64,8 @@ class Options(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("sweep_launches", C.c_int64),
                 ("segments_per_sweep", C.c_int64), ("unique_segments", C.c_int64),
-                ("device_bytes", C.c_int64), ("items", C.c_int64 * 2)]
+                ("device_bytes", C.c_int64), ("items", C.c_int64 * 2), ("kernel", C.c_int64),
+                ("swept_segments", C.c_int64)]
 
 
 def problem_from_arrays(arrays):
@@ -261,7 +262,8 @@ class Sweeper:
         self._ck(self.lib.mocb200_get_stats(self.h, C.byref(s)), "get_stats")
         return {"kernel_launches": s.kernel_launches, "sweep_launches": s.sweep_launches,
                 "segments_per_sweep": s.segments_per_sweep, "unique_segments": s.unique_segments,
-                "device_bytes": s.device_bytes, "items": [s.items[0], s.items[1]]}
+                "device_bytes": s.device_bytes, "items": [s.items[0], s.items[1]], "kernel": s.kernel,
+                "swept_segments": s.swept_segments}
 
     def set_timing(self, enabled=True):
         self._ck(self.lib.mocb200_set_timing(self.h, int(enabled)), "set_timing")

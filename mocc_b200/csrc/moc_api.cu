@@ -487,6 +487,8 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                 xptr[(size_t)(pbegin[t] + k0) / 4] = make_int2(cf, bw_first[k0 / 4]);
             }
         }
+        xcross.push_back(sentinel); // the kernels read up to two entries past the one they test
+        xcross.push_back(sentinel);
         int rc2;
         if ((rc2 = dev_upload(h, &h->d_pseg_len, plen)) || (rc2 = dev_upload(h, &h->d_pseg_fsr, pfsr)) ||
             (rc2 = dev_upload(h, &h->d_xptr, xptr)) || (rc2 = dev_upload(h, &h->d_xcross, xcross)))
@@ -754,6 +756,9 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     if ((rc = dev_alloc(h, &h->d_qg, (size_t)p.n_group * p.n_reg)) || (rc = dev_alloc(h, &h->d_tg, (size_t)p.n_group * p.n_reg)))
         return rc;
     h->stats.device_bytes = h->device_bytes;
+    h->stats.kernel       = h->kernel;
+    for (const auto &tl : h->tlists)
+        h->stats.swept_segments += tl.segs / std::max(1, tl.np) / std::max(1, tl.n_planes);
     return MOCB200_OK;
 }
 
@@ -804,17 +809,26 @@ WarpFn pick_warp_kernel(int gl, int np, int tally, bool cached)
 
 typedef void (*ChunkFn)(const ChunkArgs);
 
-ChunkFn pick_chunk_kernel(int np, int nw)
+template <int NW, int TALLY> ChunkFn pick_chunk_np(int np)
 {
-    switch (np * 2 + (nw == 2 ? 1 : 0)) {
-    case 2: return sweep_chunk_kernel<1, 1>;
-    case 3: return sweep_chunk_kernel<1, 2>;
-    case 4: return sweep_chunk_kernel<2, 1>;
-    case 5: return sweep_chunk_kernel<2, 2>;
-    case 6: return sweep_chunk_kernel<3, 1>;
-    case 7: return sweep_chunk_kernel<3, 2>;
-    case 8: return sweep_chunk_kernel<4, 1>;
-    case 9: return sweep_chunk_kernel<4, 2>;
+    switch (np) {
+    case 1: return sweep_chunk_kernel<1, NW, TALLY>;
+    case 2: return sweep_chunk_kernel<2, NW, TALLY>;
+    case 3: return sweep_chunk_kernel<3, NW, TALLY>;
+    case 4: return sweep_chunk_kernel<4, NW, TALLY>;
+    }
+    return nullptr;
+}
+
+ChunkFn pick_chunk_kernel(int np, int nw, int tally)
+{
+    switch ((nw == 2 ? 3 : 0) + tally) {
+    case 0: return pick_chunk_np<1, 0>(np);
+    case 1: return pick_chunk_np<1, 1>(np);
+    case 2: return pick_chunk_np<1, 2>(np);
+    case 3: return pick_chunk_np<2, 0>(np);
+    case 4: return pick_chunk_np<2, 1>(np);
+    case 5: return pick_chunk_np<2, 2>(np);
     }
     return nullptr;
 }
@@ -949,8 +963,9 @@ int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb
         }
     for (int np = 1; np <= kMaxPolar && e == cudaSuccess; np++)
         for (int nw = 1; nw <= kChunkMaxTeam && e == cudaSuccess; nw++)
-            e = cudaFuncSetAttribute((const void *)pick_chunk_kernel(np, nw), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kChunkSmemBudget);
+            for (int t = 0; t < 3 && e == cudaSuccess; t++)
+                e = cudaFuncSetAttribute((const void *)pick_chunk_kernel(np, nw, t),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kChunkSmemBudget);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute((const void *)exp_cache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -1290,7 +1305,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
                 a.cache = tl.d_cache, a.list_pseg = tl.pseg, a.cache_groups = h->G;
                 a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
-                if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1 && tally == MOCB200_TALLY_NONE) {
+                if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1) {
                     int caps = 0, nw = 1, teams = 1;
                     chunk_geometry(tl.max_nseg, tl.np, h->opt.chunk_cap, &caps, &nw, &teams);
                     if (h->opt.chunk_cap < 0) // test hook: negative cap = that cap with two-warp teams
@@ -1306,7 +1321,12 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                     c.q = h->d_qg, c.tally = h->d_tg, c.bc_in = bc_in, c.bc_out = bc_out;
                     c.scratch = h->d_scratch, c.scratch_per_warp = h->scratch_per_warp;
                     c.cache = tl.d_cache, c.list_pseg = tl.pseg, c.cache_groups = h->G, c.caps = caps;
-                    pick_chunk_kernel(tl.np, nw)<<<cgrid, 32 * nw * teams, teams * chunk_warp_bytes(caps, tl.np),
+                    static const char *ex_mode = getenv("MOCB200_CHUNK_EX"); // tuning hook
+                    c.ex_mode = ex_mode && ex_mode[0] == '1' ? 1 : 0;
+                    c.xptr = h->d_xptr, c.cross = h->d_xcross, c.cur_w = h->d_curw, c.flx_w = h->d_flxw;
+                    c.plane_surf_offset = h->d_plane_surf_offset, c.current = h->d_current, c.surface_flux = h->d_surfflux;
+                    c.dsum = h->d_dsum, c.ssum = h->d_ssum, c.n_surf_plane = h->n_surf_plane, c.n_plane_total = h->n_plane;
+                    pick_chunk_kernel(tl.np, nw, tally)<<<cgrid, 32 * nw * teams, teams * chunk_warp_bytes(caps, tl.np),
                                                    h->stream>>>(c);
                 } else {
                     pick_warp_kernel(gl, tl.np, tally, cached)<<<grid, kWarpBlock, cached ? 0 : track_smem_bytes(h),

@@ -229,7 +229,154 @@ struct ChunkArgs {
     int64_t list_pseg;
     int32_t cache_groups;
     int32_t caps; // segments a team stages at once
+    int32_t ex_mode; // 0: attenuations by TMA bulk copy, 1: by 16-byte cp.async of all lanes (tuning)
+    // coarse-mesh tallies of the last inner (TALLY 1: moc::Current, 2: cmdo::CurrentCorrections)
+    const int2 *xptr;   // per 4 padded segments: first forward / backward crossing index
+    const Cross *cross; // crossing lists with sentinels
+    const double *cur_w, *flx_w; // [n_plane][n_ang][2]
+    const int32_t *plane_surf_offset;
+    double *current, *surface_flux; // [n_surf][GP]
+    double *dsum; // psi_diff per FSR, angle and direction: [g][n_reg][2 n_ang]
+    double *ssum; // psi per crossing: [g][plane][n_ang][n_surf_plane][2]
+    int32_t n_surf_plane, n_plane_total;
 };
+
+// what the tally variants of the walk need beside the staged data
+struct ChunkTallyCtx {
+    const ChunkArgs *a;
+    const int32_t *fb; // FSR ids of the staged block (plane-local)
+    int seg_begin, nseg, k_off; // track position of the staged block
+    int plane, first_reg, grel, g;
+    int ang[4];
+};
+
+// The walk of the last inner: as chunk_walk, plus moc::Current::post_ray (moc_current_worker.hpp:202-264)
+// or cmdo::CurrentCorrections::post_ray (correction_worker.hpp:109-205) at the coarse-surface crossings the
+// lane's chunk contains. The two directions are walked one after the other.
+template <int P, int TALLY>
+__device__ __forceinline__ void chunk_walk_tally(const double *exb, const double *qb, double *ab, int lo, int hi,
+                                                 const double (&wt)[P], double (&psi_f)[P], double (&psi_b)[P],
+                                                 const ChunkTallyCtx &c)
+{
+    const ChunkArgs &a = *c.a;
+    if (lo >= hi)
+        return;
+    const int GP    = a.GP;
+    const int nslot = 2 * a.n_ang;
+    double cw[P][2], fw[P][2];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        const size_t o = ((size_t)c.plane * a.n_ang + c.ang[p]) * 2;
+        cw[p][0] = a.cur_w[o], cw[p][1] = a.cur_w[o + 1];
+        fw[p][0] = a.flx_w[o], fw[p][1] = a.flx_w[o + 1];
+    }
+    const int surf_off = a.plane_surf_offset[c.plane];
+    auto tally_cross = [&](const Cross &x, const double (&psi)[P], int dir) {
+        const int norm = x.surf & 1;
+        const int surf = x.surf >> 1;
+        const size_t o = (size_t)(surf + surf_off) * GP + c.g;
+        double cs = 0.0, fsum = 0.0;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            cs   = fma(psi[p], cw[p][norm], cs);
+            fsum = fma(psi[p], fw[p][norm], fsum);
+        }
+        // forward adds, backward subtracts (moc_current_worker.hpp:230-231); the corrections worker also
+        // subtracts the backward SURFACE FLUX (correction_worker.hpp:136-137, 194-195)
+        atomicAdd(&a.current[o], dir ? -cs : cs);
+        atomicAdd(&a.surface_flux[o], (dir && TALLY == 2) ? -fsum : fsum);
+        if (TALLY == 2) {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const size_t so = (size_t)c.grel * a.n_plane_total * a.n_ang * a.n_surf_plane * 2 +
+                                  (((size_t)c.plane * a.n_ang + c.ang[p]) * a.n_surf_plane + surf) * 2 + dir;
+                atomicAdd(&a.ssum[so], psi[p]);
+            }
+        }
+    };
+    auto dsum_add = [&](int reg, int p, int dir, double d) {
+        const size_t o = (size_t)c.grel * a.n_reg * nslot + (size_t)reg * nslot + c.ang[p] * 2 + dir;
+        atomicAdd(&a.dsum[o], d);
+    };
+    const int nseg = c.nseg;
+    // first crossings at or after the chunk's first node, in either walk order
+    const int kt_lo = c.k_off + lo, kt_hi = c.k_off + hi; // track positions [kt_lo, kt_hi)
+    // (the lists are walked through a three-deep register queue so that the dependent global loads of the
+    // next crossings overlap the segments in between; the lists end in sentinels and the array is padded)
+    int ci_f = a.xptr[(c.seg_begin + (kt_lo & ~3)) >> 2].x;
+    int ci_b = a.xptr[(c.seg_begin + ((kt_hi - 1) & ~3)) >> 2].y;
+    Cross xf = a.cross[ci_f], xf1 = a.cross[ci_f + 1], xf2 = a.cross[ci_f + 2];
+    Cross xb = a.cross[ci_b], xb1 = a.cross[ci_b + 1], xb2 = a.cross[ci_b + 2];
+    auto next_f = [&]() {
+        xf = xf1, xf1 = xf2;
+        ++ci_f;
+        xf2 = a.cross[ci_f + 2];
+    };
+    auto next_b = [&]() {
+        xb = xb1, xb1 = xb2;
+        ++ci_b;
+        xb2 = a.cross[ci_b + 2];
+    };
+    while (xf.node < kt_lo)
+        next_f();
+    while (xb.node < nseg - kt_hi)
+        next_b();
+    // ---- forward ----
+    for (int k = lo; k < hi; k++) {
+        const int kt = c.k_off + k; // forward flux at the node in front of segment kt
+        while (xf.node == kt) {
+            tally_cross(xf, psi_f, 0);
+            next_f();
+        }
+        double e[P];
+        load_ex<P>(exb, k, e);
+        const double q = qb[k];
+        double sf = 0.0;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const double d = (psi_f[p] - q) * (1.0 - e[p]);
+            psi_f[p] -= d;
+            sf = fma(d, wt[p], sf);
+            if (TALLY == 2)
+                dsum_add(c.fb[k] + c.first_reg, p, 0, d);
+        }
+        ab[k] = sf;
+        if (kt == nseg - 1) { // far end of the ray
+            while (xf.node == nseg) {
+                tally_cross(xf, psi_f, 0);
+                next_f();
+            }
+        }
+    }
+    // ---- backward ----
+    for (int k = hi - 1; k >= lo; k--) {
+        const int kt = c.k_off + k;
+        const int nb = nseg - 1 - kt; // segments walked by the backward sweep so far
+        while (xb.node == nb) {
+            tally_cross(xb, psi_b, 1);
+            next_b();
+        }
+        double e[P];
+        load_ex<P>(exb, k, e);
+        const double q = qb[k];
+        double sr = ab[k];
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const double d = (psi_b[p] - q) * (1.0 - e[p]);
+            psi_b[p] -= d;
+            sr = fma(d, wt[p], sr);
+            if (TALLY == 2)
+                dsum_add(c.fb[k] + c.first_reg, p, 1, d);
+        }
+        ab[k] = sr;
+        if (kt == 0) { // near end of the ray
+            while (xb.node == nseg) {
+                tally_cross(xb, psi_b, 1);
+                next_b();
+            }
+        }
+    }
+}
 
 // A work item as the team sees it: filled asynchronously (cp.async) one item ahead, in shared memory
 struct __align__(16) ChunkWork {
@@ -240,7 +387,7 @@ struct __align__(16) ChunkWork {
 };
 
 // NW warps ("team") cooperate on one track: 32 NW lanes, each owning one contiguous chunk.
-template <int P, int NW>
+template <int P, int NW, int TALLY>
 __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(const ChunkArgs a)
 {
     constexpr int T = 32 * NW; // lanes of a team
@@ -328,7 +475,14 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
         }
     };
     auto issue_ex = [&](const ChunkWork *k, int k_off, int n) {
-        if (leader) {
+        if (a.ex_mode == 1) {
+            const int g        = a.g_begin + k->grel;
+            const double *ex_g = a.cache + (((size_t)k->ipl * a.cache_groups + g) * a.list_pseg + k->u.cpos + k_off) * P;
+            const int n16      = ((n + 3) & ~3) * P / 2;
+#pragma unroll 4
+            for (int i = tl; i < n16; i += T)
+                cp_async_16(exb + 2 * i, ex_g + 2 * i);
+        } else if (leader) {
             const int g        = a.g_begin + k->grel;
             const double *ex_g = a.cache + (((size_t)k->ipl * a.cache_groups + g) * a.list_pseg + k->u.cpos) * P;
             const uint32_t bytes = (uint32_t)((n + 3) & ~3) * (uint32_t)P * 8u;
@@ -350,8 +504,10 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
             cp_async_8(qb + i, qf + fb[i]);
     };
     auto wait_staged = [&]() {
-        mbar_wait(bar + 2, par_e);
-        par_e ^= 1u;
+        if (a.ex_mode == 0) {
+            mbar_wait(bar + 2, par_e);
+            par_e ^= 1u;
+        }
         cp_async_wait_all();
         team_sync();
     };
@@ -365,8 +521,8 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
     // One staged (super-)block. cf: forward flux entering the block (team-uniform), eb: backward flux entering
     // it from the far side. Leaves the contributions in ab; returns the forward flux leaving the block
     // (valid in the last lane of the team) and the backward flux leaving it (valid in team lane 0).
-    auto block = [&](int n, const double (&wt)[P], const double (&cf)[P], const double (&eb)[P], double (&out_fwd)[P],
-                     double (&out_bwd)[P]) {
+    auto block = [&](int n, int k_off, int fi, const ChunkWork *k, const double (&wt)[P], const double (&cf)[P],
+                     const double (&eb)[P], double (&out_fwd)[P], double (&out_bwd)[P]) {
         const int L  = ((n + T - 1) / T) | 1;
         const int lo = min(tl * L, n), hi = min(lo + L, n);
         double A[P], Af[P], Bf[P], Ab[P], Bb[P];
@@ -416,7 +572,18 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
             psi_b[p]   = lane == 31 ? ebw[p] : in_b;
             out_fwd[p] = of;
         }
-        chunk_walk<P>(exb, qb, ab, lo, hi, wt, psi_f, psi_b);
+        if (TALLY == 0) {
+            chunk_walk<P>(exb, qb, ab, lo, hi, wt, psi_f, psi_b);
+        } else {
+            ChunkTallyCtx c;
+            c.a = &a, c.fb = fbuf + fi * caps;
+            c.seg_begin = k->u.seg_begin, c.nseg = k->u.nseg, c.k_off = k_off;
+            c.plane = k->pinfo.x, c.first_reg = k->pinfo.y, c.grel = k->grel, c.g = a.g_begin + k->grel;
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                c.ang[p] = k->u.ang[p];
+            chunk_walk_tally<P, TALLY>(exb, qb, ab, lo, hi, wt, psi_f, psi_b, c);
+        }
 #pragma unroll
         for (int p = 0; p < P; p++)
             out_bwd[p] = psi_b[p];
@@ -456,7 +623,7 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
     int fi      = 0;     // FSR-id buffer of `cur`
 
     while (w_cur < total) {
-        const uint32_t w_nn_raw = fetch(); // consumed at the end of this item
+        uint32_t w_nn_raw; // work index two items ahead: fetched once the staging loads have drained, consumed at the end
         const ChunkWork *cur = &s_work[team][cs];
         ChunkWork *nxt       = &s_work[team][cs ^ 1];
         const bool have_nxt  = w_nxt < total;
@@ -474,6 +641,7 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
                 gather_q(fi, cur, nseg);
             }
             wait_staged(); // also: the next item's descriptor and this item's boundary flux have landed
+            w_nn_raw = fetch();
             const bool pre = have_nxt && nxt->u.nseg <= caps;
             if (pre)
                 issue_fsr(fi ^ 1, nxt, 0, nxt->u.nseg);
@@ -483,7 +651,7 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
 #pragma unroll
             for (int p = 0; p < P; p++)
                 wt[p] = cur->wt[p], cf[p] = cur->cf[p], cb[p] = cur->cb[p];
-            block(nseg, wt, cf, cb, cf_out, cb_out);
+            block(nseg, 0, fi, cur, wt, cf, cb, cf_out, cb_out);
             team_sync();
             if (pre) { // exb and qb are free again: stage the next track behind this one's reductions
                 issue_ex(nxt, 0, nxt->u.nseg);
@@ -497,6 +665,7 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
             // ================= long track: super-blocks of caps segments chained by a carried flux =================
             cp_async_wait_all();
             team_sync();
+            w_nn_raw = fetch();
             if (have_nxt)
                 prefetch_flux(nxt);
             const int nsb = (nseg + caps - 1) / caps;
@@ -562,7 +731,7 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
 #pragma unroll
                 for (int p = 0; p < P; p++)
                     eb[p] = sb > 0 ? sc[sb * P + p] : cb[p];
-                block(n, wt, cf, eb, of, ob);
+                block(n, sb * caps, fi, cur, wt, cf, eb, of, ob);
 #pragma unroll
                 for (int p = 0; p < P; p++) {
                     if (NW > 1) { // the last lane of the team holds the flux leaving the block

@@ -90,15 +90,15 @@ def test_chunk_kernel_superblocks_match_reference_golden(case, max_polar, chunk_
     flat, gold = load_case(case)
     gs = bool(gold["gs_boundary"][0])
     sw = _sweeper(flat, boundary_update=0 if gs else 1, max_polar=max_polar, kernel=4, chunk_cap=chunk_cap)
-    n = 0
+    xy = _xy_mask(flat)
     for rec in records(gold):
-        if int(rec["mode"][0]) != 0:
-            continue
-        flux, bc_out, _, _ = _run_record(sw, flat, rec)
+        flux, bc_out, cur, sf = _run_record(sw, flat, rec)
         _close(flux, rec["flux_out"])
         _close(bc_out, rec["bc_out"])
-        n += 1
-    assert n > 0
+        if cur is not None:
+            area = flat["surf_area"]
+            _close(cur[xy] / area[xy], rec["current"][xy], atol=1e-13)
+            _close(sf[xy] / area[xy], rec["surface_flux"][xy], atol=1e-13)
     sw.close()
 
 
@@ -146,7 +146,7 @@ def test_batched_groups_match_oracle(case, jacobi, kernel):
     sw.close()
 
 
-@pytest.mark.parametrize("kernel", [2, 3])
+@pytest.mark.parametrize("kernel", [2, 3, 4, -4])
 @pytest.mark.parametrize("max_polar", [1, 2])
 def test_corrections_match_reference_golden(kernel, max_polar):
     """MOCB200_TALLY_CORRECTIONS == the reference's MoCSweeper_2D3D last inner (cmdo::CurrentCorrections):
@@ -155,7 +155,9 @@ def test_corrections_match_reference_golden(kernel, max_polar):
     flat, gold = load_case("mini3d_2d3d")
     recs = [r for r in records(gold) if int(r["mode"][0]) == 2]
     assert recs
-    sw = _sweeper(flat, boundary_update=0, kernel=kernel, max_polar=max_polar)
+    # kernel -4: the chunk kernel with a 64-segment staging cap and two-warp teams (super-block chaining)
+    kw = dict(kernel=4, chunk_cap=-64) if kernel == -4 else dict(kernel=kernel)
+    sw = _sweeper(flat, boundary_update=0, max_polar=max_polar, **kw)
     xy = _xy_mask(flat)
     area = flat["surf_area"]
     n_plane = sw.n_plane
