@@ -402,7 +402,8 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
     const int wid  = threadIdx.x >> 5;
     const int team = wid / NW, wl = wid - team * NW;
     const int tl   = wl * 32 + lane; // lane within the team
-    const bool leader = tl == 0;
+    const bool leader = tl == 0;          // work counter, backward exit flux
+    const bool loader = tl == T - 32;     // first lane of the team's last warp: issues the TMA copies
     char *wbase    = reinterpret_cast<char *>(s_dyn) + (size_t)team * chunk_warp_bytes(caps, P);
     double *exb    = reinterpret_cast<double *>(wbase);
     double *qb     = exb + (size_t)caps * P;
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
     // ---- asynchronous two-level prefetch of a work item into its shared-memory slot ----
     // level 1: descriptor and plane info (addresses depend on the work index only)
     auto prefetch_unit = [&](uint32_t w, ChunkWork *k) {
-        if (wl == 0 && lane < 8) {
+        if (wl == NW - 1 && lane < 8) {
             const uint32_t unit_id = w / per_unit;
             const uint32_t r       = w - unit_id * per_unit;
             const uint32_t ipl     = r / (uint32_t)a.g_count;
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
     // level 2 (descriptor visible): angle weights and incoming boundary flux. Boundary values read here are
     // never written by the same launch (a launch is one boundary phase / one Jacobi buffer).
     auto prefetch_flux = [&](ChunkWork *k) {
-        if (wl == 0 && lane < 12) {
+        if (wl == NW - 1 && lane < 12) {
             const int p = lane & 3, kind = lane >> 2;
             if (p < P) {
                 const int g     = a.g_begin + k->grel;
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
     };
     // TMA bulk copies of one (super-)block: FSR ids into buffer fi, attenuations into exb
     auto issue_fsr = [&](int fi, const ChunkWork *k, int k_off, int n) {
-        if (leader) {
+        if (loader) {
             const uint32_t bytes = (uint32_t)((n + 3) & ~3) * 4u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar + fi, bytes);
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
 #pragma unroll 4
             for (int i = tl; i < n16; i += T)
                 cp_async_16(exb + 2 * i, ex_g + 2 * i);
-        } else if (leader) {
+        } else if (loader) {
             const int g        = a.g_begin + k->grel;
             const double *ex_g = a.cache + (((size_t)k->ipl * a.cache_groups + g) * a.list_pseg + k->u.cpos) * P;
             const uint32_t bytes = (uint32_t)((n + 3) & ~3) * (uint32_t)P * 8u;
