@@ -226,17 +226,13 @@ def main():
         nonlocal h2d, d2h
         groups = [range(G)] if args.mode == "batched" else [[g] for g in range(G)]
         for gl in groups:
+            # what the C++ plugin does around every sweep(group): one fused upload (source, flux, incoming
+            # boundary flux), the sweep, one fused download (flux, boundary flux, coarse tallies)
             for g in gl:
-                sw.set_source(g, src[g])
-                sw.set_flux(g, flux_h[g])
-                for ip in range(n_plane):
-                    sw.set_boundary(ip, g, bc_h[ip][g])
+                sw.set_sweep_inputs(g, src[g], flux_h[g], [bc_h[ip][g] for ip in range(n_plane)])
             sw.sweep(gl[0], len(gl), n_inner=n_inner, tally_mode=TALLY_CURRENT)
             for g in gl:
-                sw.get_flux(g, 1, out=flux_h[g:g + 1])
-                for ip in range(n_plane):
-                    bc_h[ip][g] = sw.get_boundary(ip, g, 1)[0]
-                sw.get_coarse(g)
+                sw.get_sweep_results(g, flux_h[g], [bc_h[ip][g] for ip in range(n_plane)], coarse=True)
         if count:
             h2d = G * 8 * (2 * n_reg + n_plane * bcpg)
             d2h = G * 8 * (n_reg + n_plane * bcpg + 2 * n_surf)

@@ -205,6 +205,20 @@ int mocb200_get_boundary(mocb200_sweeper *h, int plane, int g_begin, int g_count
  */
 int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int tally_mode, int use_qbar);
 
+/* The transfers of one sweep(group) call fused (one staging copy each way, ONE synchronisation):
+ * what MoCSweeper::sweep reads from / leaves in the host objects around sweep1g
+ * (moc_sweeper.cpp:197-219: source_->get(), flux_(:, group), boundary_[plane]).
+ *   set_sweep_inputs : source[n_reg], flux[n_reg] (either may be NULL = keep the device copy) and, for every
+ *                      macroplane ip of the mesh, boundary[ip] -> [bc_per_group] incoming boundary flux
+ *                      (boundary NULL or entry NULL = keep); planes outside this handle's range are ignored.
+ *                      Returns once the host arrays may be reused; the copy is stream-ordered before the sweep.
+ *   get_sweep_results: flux[n_reg] (only this handle's FSR range is written), boundary[ip] as above,
+ *                      current/surface_flux[n_surf] as mocb200_get_coarse (both NULL = skip). Synchronises. */
+int mocb200_set_sweep_inputs(mocb200_sweeper *h, int group, const double *source, const double *flux,
+                             const double *const *boundary);
+int mocb200_get_sweep_results(mocb200_sweeper *h, int group, double *flux, double *const *boundary, double *current,
+                              double *surface_flux);
+
 /* Raw radial coarse tallies of the last TALLY_CURRENT/CORRECTIONS sweep for one group:
  * current[n_surf], surface_flux[n_surf] (whole-mesh surface indexing, x/y-normal surfaces of
  * this handle's macroplanes only, NOT yet divided by the surface area -- the reference does

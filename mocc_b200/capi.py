@@ -126,6 +126,8 @@ def load_library(path=None):
     lib.mocb200_get_coarse.argtypes = [H, C.c_int, _f64p, _f64p]
     lib.mocb200_set_sn_xs.argtypes = [H, C.c_int, C.c_int, _f64p]
     lib.mocb200_get_corrections.argtypes = [H, C.c_int, _f64p, _f64p]
+    lib.mocb200_set_sweep_inputs.argtypes = [H, C.c_int, _f64p, _f64p, C.POINTER(_f64p)]
+    lib.mocb200_get_sweep_results.argtypes = [H, C.c_int, _f64p, C.POINTER(_f64p), _f64p, _f64p]
     lib.mocb200_get_stats.argtypes = [H, C.POINTER(Stats)]
     lib.mocb200_last_sweep_ms.argtypes = [H, _f64p]
     lib.mocb200_set_timing.argtypes = [H, C.c_int]
@@ -256,6 +258,45 @@ class Sweeper:
             beta = np.full((n_ang2, n), np.nan)
         self._ck(self.lib.mocb200_get_corrections(self.h, group, _ptr(alpha), _ptr(beta)), "get_corrections")
         return alpha, beta
+
+    def set_sweep_inputs(self, group, source=None, flux=None, boundary=None):
+        """Fused upload for one sweep(group): source[n_reg], flux[n_reg], boundary = list of per-plane
+        [bc_per_group] arrays (None entries skipped). One staged copy, no synchronisation."""
+        keep = []
+
+        def arr(a, n):
+            if a is None:
+                return None
+            a = _host(a, (n,))
+            keep.append(a)
+            return _ptr(a)
+        bptr = None
+        if boundary is not None:
+            bptr = (_f64p * self.n_plane)()
+            for ip, b in enumerate(boundary):
+                if b is not None:
+                    bptr[ip] = arr(b, self.bc_per_group)
+        self._ck(self.lib.mocb200_set_sweep_inputs(self.h, group, arr(source, self.n_reg), arr(flux, self.n_reg), bptr),
+                 "set_sweep_inputs")
+
+    def get_sweep_results(self, group, flux=None, boundary=None, coarse=False):
+        """Fused download after one sweep(group): fills flux[n_reg] and the per-plane boundary arrays in place
+        (None = skip) and returns (current, surface_flux) when coarse; one synchronisation."""
+        bptr = None
+        if boundary is not None:
+            bptr = (_f64p * self.n_plane)()
+            for ip, b in enumerate(boundary):
+                if b is not None:
+                    assert b.dtype == np.float64 and b.flags.c_contiguous and b.size == self.bc_per_group
+                    bptr[ip] = _ptr(b)
+        if flux is not None:
+            assert flux.dtype == np.float64 and flux.flags.c_contiguous and flux.size == self.n_reg
+        cur = np.empty(self.n_surf) if coarse else None
+        sf = np.empty(self.n_surf) if coarse else None
+        self._ck(self.lib.mocb200_get_sweep_results(self.h, group, _ptr(flux) if flux is not None else None, bptr,
+                                                    _ptr(cur) if coarse else None, _ptr(sf) if coarse else None),
+                 "get_sweep_results")
+        return cur, sf
 
     def stats(self):
         s = Stats()

@@ -83,6 +83,11 @@ struct mocb200_sweeper {
     double *d_stage   = nullptr; // staging for column <-> [n][GP] transposes
     size_t stage_elems = 0;
     double *h_stage    = nullptr; // pinned
+    // fused per-sweep transfers: one pinned + one device buffer each way
+    double *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
+    size_t io_elems = 0;
+    cudaEvent_t ev_in = nullptr; // the last fused upload has left h_in
+    bool ev_in_pending = false;
     uint32_t *d_counters = nullptr;
     int n_counters       = 0;
     std::vector<WorkList> lists;
@@ -748,6 +753,12 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     if ((rc = dev_alloc(h, &h->d_stage, h->stage_elems)))
         return rc;
     CUDA_TRY(h, cudaMallocHost((void **)&h->h_stage, h->stage_elems * sizeof(double)));
+    h->io_elems = 2 * (size_t)p.n_reg + (size_t)(h->plane_end - h->plane_begin) * p.bc_per_group + 2 * (size_t)p.n_surf;
+    if ((rc = dev_alloc(h, &h->d_in, h->io_elems)) || (rc = dev_alloc(h, &h->d_out, h->io_elems)))
+        return rc;
+    CUDA_TRY(h, cudaMallocHost((void **)&h->h_in, h->io_elems * sizeof(double)));
+    CUDA_TRY(h, cudaMallocHost((void **)&h->h_out, h->io_elems * sizeof(double)));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
     h->n_counters = (int)(h->lists.size() + h->tlists.size());
     if ((rc = dev_alloc(h, &h->d_counters, (size_t)h->n_counters)))
         return rc;
@@ -1005,6 +1016,12 @@ int mocb200_destroy(mocb200_sweeper *h)
             cudaFree(q);
     if (h->h_stage)
         cudaFreeHost(h->h_stage);
+    if (h->h_in)
+        cudaFreeHost(h->h_in);
+    if (h->h_out)
+        cudaFreeHost(h->h_out);
+    if (h->ev_in)
+        cudaEventDestroy(h->ev_in);
     for (auto &pr : h->ev_pool) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -1368,6 +1385,112 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
             h->d_flux, h->reg_lo, h->reg_hi, group_major ? 1 : 0);
         h->stats.kernel_launches++;
         CUDA_TRY(h, cudaGetLastError());
+    }
+    return MOCB200_OK;
+}
+
+int mocb200_set_sweep_inputs(mocb200_sweeper *h, int group, const double *source, const double *flux,
+                             const double *const *boundary)
+{
+    int rc = check_groups(h, group, 1);
+    if (rc)
+        return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->ev_in_pending) { // the previous fused upload must have left the pinned buffer
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_in));
+        h->ev_in_pending = false;
+    }
+    const size_t nr = (size_t)h->n_reg, nb = (size_t)h->bcpg;
+    size_t off = 0;
+    const size_t o_src = off;
+    if (source) {
+        std::memcpy(h->h_in + off, source, nr * sizeof(double));
+        off += nr;
+    }
+    const size_t o_flux = off;
+    if (flux) {
+        std::memcpy(h->h_in + off, flux, nr * sizeof(double));
+        off += nr;
+    }
+    const size_t o_bc = off;
+    std::vector<int> bc_planes;
+    for (int ip = h->plane_begin; boundary && ip < h->plane_end; ip++) {
+        if (!boundary[ip])
+            continue;
+        std::memcpy(h->h_in + off, boundary[ip], nb * sizeof(double));
+        off += nb;
+        bc_planes.push_back(ip);
+    }
+    if (off == 0)
+        return MOCB200_OK;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, off * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_in, h->stream));
+    h->ev_in_pending = true;
+    auto scatter = [&](const double *cols, int64_t n, double *dst) {
+        scatter_columns_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, h->stream>>>(n, h->GP, group, 1, cols, dst);
+        h->stats.kernel_launches++;
+    };
+    if (source)
+        scatter(h->d_in + o_src, h->n_reg, h->d_src);
+    if (flux)
+        scatter(h->d_in + o_flux, h->n_reg, h->d_flux);
+    for (size_t i = 0; i < bc_planes.size(); i++) {
+        const size_t poff = (size_t)bc_planes[i] * h->bcpg * h->GP;
+        scatter(h->d_in + o_bc + i * nb, h->bcpg, h->d_bc[0] + poff);
+        if (h->d_bc[1] != h->d_bc[0]) // Jacobi: PRESCRIBED faces are never rewritten, keep both copies alike
+            scatter(h->d_in + o_bc + i * nb, h->bcpg, h->d_bc[1] + poff);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return MOCB200_OK;
+}
+
+int mocb200_get_sweep_results(mocb200_sweeper *h, int group, double *flux, double *const *boundary, double *current,
+                              double *surface_flux)
+{
+    int rc = check_groups(h, group, 1);
+    if (rc)
+        return rc;
+    if ((current == nullptr) != (surface_flux == nullptr))
+        return fail(h, MOCB200_ERR_INVALID, "get_sweep_results: current and surface_flux go together");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t nr = (size_t)(h->reg_hi - h->reg_lo), nb = (size_t)h->bcpg, ns = (size_t)h->n_surf;
+    auto gather = [&](const double *src, int64_t n, double *cols) {
+        gather_columns_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, h->stream>>>(n, h->GP, group, 1, src, cols);
+        h->stats.kernel_launches++;
+    };
+    size_t off = 0;
+    const size_t o_flux = off;
+    if (flux) {
+        gather(h->d_flux + (size_t)h->reg_lo * h->GP, (int64_t)nr, h->d_out + off);
+        off += nr;
+    }
+    const size_t o_bc = off;
+    std::vector<int> bc_planes;
+    for (int ip = h->plane_begin; boundary && ip < h->plane_end; ip++) {
+        if (!boundary[ip])
+            continue;
+        gather(h->d_bc[h->bc_cur] + (size_t)ip * h->bcpg * h->GP, h->bcpg, h->d_out + off);
+        off += nb;
+        bc_planes.push_back(ip);
+    }
+    const size_t o_cur = off;
+    if (current) {
+        gather(h->d_current, h->n_surf, h->d_out + off);
+        gather(h->d_surfflux, h->n_surf, h->d_out + off + ns);
+        off += 2 * ns;
+    }
+    if (off == 0)
+        return MOCB200_OK;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, off * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (flux)
+        std::memcpy(flux + h->reg_lo, h->h_out + o_flux, nr * sizeof(double));
+    for (size_t i = 0; i < bc_planes.size(); i++)
+        std::memcpy(boundary[bc_planes[i]], h->h_out + o_bc + i * nb, nb * sizeof(double));
+    if (current) {
+        std::memcpy(current, h->h_out + o_cur, ns * sizeof(double));
+        std::memcpy(surface_flux, h->h_out + o_cur + ns, ns * sizeof(double));
     }
     return MOCB200_OK;
 }

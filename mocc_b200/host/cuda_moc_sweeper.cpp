@@ -167,22 +167,20 @@ void CudaMoCSweeper::upload_group(int group)
     if (send_xs)
         std::copy(xstr_.xs().begin(), xstr_.xs().end(), col_.begin());
     const VectorX &src = source_->get();
-    for (const Part &p : parts_) {
-        if (send_xs)
+    if (send_xs)
+        for (const Part &p : parts_)
             check(p, mocb200_set_xs(p.h, group, 1, col_.data(), &xstr_true_fsr_[(size_t)group * n_reg_],
                                     &xs_self_fsr_[(size_t)group * n_reg_]),
                   "mocb200_set_xs");
-        check(p, mocb200_set_source(p.h, group, 1, src.data()), "mocb200_set_source");
-    }
     xs_uploaded_[group] = true;
     for (int ireg = 0; ireg < (int)n_reg_; ireg++)
         col_[ireg] = flux_(ireg, group);
-    for (const Part &p : parts_) {
-        check(p, mocb200_set_flux(p.h, group, 1, col_.data()), "mocb200_set_flux");
-        for (int ip = p.plane_begin; ip < p.plane_end; ip++)
-            check(p, mocb200_set_boundary(p.h, ip, group, 1, boundary_[ip].get_boundary(group, 0).second),
-                  "mocb200_set_boundary");
-    }
+    // source, flux and incoming boundary flux in one staged copy per device (no synchronisation)
+    std::vector<const double *> bc(n_macroplane_, nullptr);
+    for (int ip = 0; ip < n_macroplane_; ip++)
+        bc[ip] = boundary_[ip].get_boundary(group, 0).second;
+    for (const Part &p : parts_)
+        check(p, mocb200_set_sweep_inputs(p.h, group, src.data(), col_.data(), bc.data()), "mocb200_set_sweep_inputs");
 }
 
 void CudaMoCSweeper::download_flux(int group)
@@ -197,18 +195,22 @@ void CudaMoCSweeper::download_flux(int group)
 // Device results of one group -> host objects the rest of MOCC reads.
 void CudaMoCSweeper::download_group(int group, int tally)
 {
-    download_flux(group);
-    for (const Part &p : parts_)
-        for (int ip = p.plane_begin; ip < p.plane_end; ip++)
-            check(p, mocb200_get_boundary(p.h, ip, group, 1, boundary_[ip].get_boundary(group, 0).second),
-                  "mocb200_get_boundary");
-    if (tally != MOCB200_TALLY_NONE) {
-        // moc_sweeper.cpp:208-215: zero the radial data, tally, flag; the raw device tallies
-        // then go through the reference's own post_sweep (sub-plane expansion and division
-        // by the surface area, moc_current_worker.hpp:272-318) so every quirk is kept.
-        coarse_data_->zero_data_radial(group);
-        for (const Part &p : parts_) {
-            check(p, mocb200_get_coarse(p.h, group, cur_.data(), sflux_.data()), "mocb200_get_coarse");
+    // flux, outgoing boundary flux and the raw coarse tallies in one staged copy and ONE synchronisation per device
+    std::vector<double *> bc(n_macroplane_, nullptr);
+    for (int ip = 0; ip < n_macroplane_; ip++)
+        bc[ip] = const_cast<double *>(boundary_[ip].get_boundary(group, 0).second);
+    const bool coarse = tally != MOCB200_TALLY_NONE;
+    if (coarse)
+        coarse_data_->zero_data_radial(group); // moc_sweeper.cpp:208-215: zero the radial data, tally, flag
+    for (const Part &p : parts_) {
+        check(p, mocb200_get_sweep_results(p.h, group, col_.data(), bc.data(), coarse ? cur_.data() : nullptr,
+                                           coarse ? sflux_.data() : nullptr),
+              "mocb200_get_sweep_results");
+        for (int ireg = p.reg_lo; ireg < p.reg_hi; ireg++)
+            flux_(ireg, group) = col_[ireg];
+        if (coarse) {
+            // the raw device tallies then go through the reference's own post_sweep (sub-plane expansion and
+            // division by the surface area, moc_current_worker.hpp:272-318) so every quirk is kept
             for (int ip = p.plane_begin; ip < p.plane_end; ip++) {
                 for (int s = mesh_.plane_surf_xy_begin(ip); s < (int)mesh_.plane_surf_end(ip); s++) {
                     coarse_data_->current(s, group)      = cur_[s];
@@ -216,6 +218,8 @@ void CudaMoCSweeper::download_group(int group, int tally)
                 }
             }
         }
+    }
+    if (coarse) {
         moc::Current cw(coarse_data_, &mesh_);
         cw.set_group(group);
         cw.post_sweep();

@@ -113,6 +113,47 @@ def test_self_scatter_then_sweep_matches_reference(case):
     sw.close()
 
 
+@pytest.mark.parametrize("case", ["mini2d_gs", "mini2d_jacobi", "mini3d_gs"])
+def test_fused_transfers_equal_the_single_calls(case):
+    """mocb200_set_sweep_inputs / get_sweep_results == set_source + set_flux + set_boundary / get_flux +
+    get_boundary + get_coarse (what the plugin moves around every sweep(group))."""
+    flat, gold = load_case(case)
+    gs = bool(gold["gs_boundary"][0])
+    n_reg, bcpg = int(flat["n_reg"][0]), int(flat["bc_per_group"][0])
+    res = []
+    for fused in (False, True):
+        sw = _sweeper(flat, boundary_update=0 if gs else 1)
+        n_plane = sw.n_plane
+        out = []
+        for rec in records(gold):
+            g = int(rec["group"][0])
+            sw.set_xs(g, rec["xstr"], xstr_src=gold[f"xs_tr_{g}"], xs_self=gold[f"xs_self_{g}"])
+            bc = rec["bc_in"].reshape(n_plane, bcpg)
+            if fused:
+                sw.set_sweep_inputs(g, rec["src"], rec["flux_in"], [bc[ip] for ip in range(n_plane)])
+            else:
+                sw.set_source(g, rec["src"])
+                sw.set_flux(g, rec["flux_in"])
+                for ip in range(n_plane):
+                    sw.set_boundary(ip, g, bc[ip])
+            sw.sweep(g, 1, n_inner=2, tally_mode=1)
+            if fused:
+                flux = np.zeros(n_reg)
+                bo = [np.zeros(bcpg) for _ in range(n_plane)]
+                cur, sf = sw.get_sweep_results(g, flux, bo, coarse=True)
+                bo = np.concatenate(bo)
+            else:
+                flux = sw.get_flux(g, 1)[0]
+                bo = np.concatenate([sw.get_boundary(ip, g, 1)[0] for ip in range(n_plane)])
+                cur, sf = sw.get_coarse(g)
+            out.append((flux, bo, cur, sf))
+        sw.close()
+        res.append(out)
+    for a, b in zip(*res):
+        for x, y in zip(a, b):
+            _close(x, y)
+
+
 @pytest.mark.parametrize("case", ["mini2d_gs", "mini3d_gs"])
 @pytest.mark.parametrize("jacobi", [False, True])
 @pytest.mark.parametrize("kernel", [1, 2, 3])
