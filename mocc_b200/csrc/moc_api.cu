@@ -457,6 +457,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
         std::vector<int32_t> pfsr((size_t)n_pseg, 0);
         std::vector<int2> xptr((size_t)(n_pseg / 4));
         std::vector<Cross> xcross;
+        std::vector<int32_t> xcross_f0((size_t)p.n_trk, 0); // per track: start of its forward list (backward follows)
         xcross.reserve(cross.size() + 2 * (size_t)p.n_trk);
         const Cross sentinel{INT32_MAX, 0};
         for (int64_t t = 0; t < p.n_trk; t++) {
@@ -465,6 +466,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
             std::copy(p.seg_len + s0, p.seg_len + s0 + nseg, plen.begin() + pbegin[t]);
             std::copy(p.seg_fsr + s0, p.seg_fsr + s0 + nseg, pfsr.begin() + pbegin[t]);
             const int32_t f0 = (int32_t)xcross.size();
+            xcross_f0[t]     = f0;
             xcross.insert(xcross.end(), cross.begin() + cross_begin_fw[t], cross.begin() + cross_begin_fw[t] + cross_n_fw[t]);
             xcross.push_back(sentinel);
             const int32_t b0 = (int32_t)xcross.size();
@@ -511,6 +513,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                     struct UnitRec {
                         TrackUnit tu;
                         int4 len_begin; // per polar angle: where that angle's own segment lengths start
+                        int64_t trk;    // representative track (crossing lists)
                     };
                     std::vector<UnitRec> recs;
                     for (size_t b = 0; b < tbundles.size(); b++) {
@@ -530,6 +533,7 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                                 lb[q] = (int32_t)pbegin[p.geom_trk_begin[(size_t)u * p.n_geom + gq] + (t - t0)];
                             }
                             r.len_begin = make_int4(lb[0], lb[1], lb[2], lb[3]);
+                            r.trk       = t;
                             recs.push_back(r);
                         }
                     }
@@ -539,9 +543,11 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                                      [](const UnitRec &x, const UnitRec &y) { return x.tu.nseg > y.tu.nseg; });
                     std::vector<TrackUnit> units;
                     std::vector<int4> len_begin;
+                    std::vector<int64_t> unit_trk;
                     for (const auto &r : recs) {
                         units.push_back(r.tu);
                         len_begin.push_back(r.len_begin);
+                        unit_trk.push_back(r.trk);
                     }
                     TrackList tl;
                     for (auto &tu : units) {
@@ -567,7 +573,10 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                         for (size_t i = 0; i < units.size(); i++) {
                             const TrackUnit &tu = units[i];
                             ChunkUnit &c = cu[i];
-                            c.seg_begin = tu.seg_begin, c.nseg = tu.nseg, c.cpos = tu.cpos, c.pad = 0;
+                            c.seg_begin = tu.seg_begin, c.nseg = tu.nseg, c.cpos = tu.cpos;
+                            c.cross_begin = xcross_f0[unit_trk[i]];
+                            c.n_fw = cross_n_fw[unit_trk[i]], c.n_bw = cross_n_bw[unit_trk[i]];
+                            c.pad0 = c.pad1 = 0;
                             for (int q = 0; q < kMaxPolar; q++) {
                                 const int ang = tbundles[tu.bundle].ang[q];
                                 c.ang[q]  = ang;
@@ -848,9 +857,9 @@ constexpr int kChunkSmemBudget = 232448 - 12288; // opt-in dynamic shared memory
 
 // launch geometry of the chunk kernel for a list: segments a team stages at once, warps per team,
 // teams per CTA
-void chunk_geometry(int max_nseg, int np, int cap_opt, int *caps, int *nw, int *teams)
+void chunk_geometry(int max_nseg, int np, int cap_opt, bool tally, int *caps, int *nw, int *teams)
 {
-    const int per_seg   = 8 * (np + 2) + 8;
+    const int per_seg   = 8 * (np + 2) + 8 + (tally ? 4 : 0);
     const int cap_limit = ((kChunkSmemBudget / 4) / per_seg) & ~31; // at least 4 tracks in flight per SM
     int c = (max_nseg + 31) & ~31;
     c = std::min(c, cap_limit);
@@ -861,7 +870,7 @@ void chunk_geometry(int max_nseg, int np, int cap_opt, int *caps, int *nw, int *
     static const char *force_nw = getenv("MOCB200_CHUNK_NW"); // tuning hook: warps per track (1 or 2)
     if (force_nw && (force_nw[0] == '1' || force_nw[0] == '2'))
         *nw = force_nw[0] - '0';
-    *teams = std::max(1, std::min<int>(kChunkMaxWarps / *nw, kChunkSmemBudget / (int)chunk_warp_bytes(c, np)));
+    *teams = std::max(1, std::min<int>(kChunkMaxWarps / *nw, kChunkSmemBudget / (int)chunk_warp_bytes(c, np, tally)));
 }
 
 int track_smem_bytes(const mocb200_sweeper *h)
@@ -1324,9 +1333,10 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
                 if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1) {
                     int caps = 0, nw = 1, teams = 1;
-                    chunk_geometry(tl.max_nseg, tl.np, h->opt.chunk_cap, &caps, &nw, &teams);
+                    const bool tl_tally = tally != MOCB200_TALLY_NONE;
+                    chunk_geometry(tl.max_nseg, tl.np, h->opt.chunk_cap, tl_tally, &caps, &nw, &teams);
                     if (h->opt.chunk_cap < 0) // test hook: negative cap = that cap with two-warp teams
-                        chunk_geometry(tl.max_nseg, tl.np, -h->opt.chunk_cap, &caps, &nw, &teams), nw = 2,
+                        chunk_geometry(tl.max_nseg, tl.np, -h->opt.chunk_cap, tl_tally, &caps, &nw, &teams), nw = 2,
                             teams = std::min(teams, kChunkMaxWarps / 2);
                     const int cgrid =
                         (int)std::max<int64_t>(1, std::min<int64_t>((warps + teams - 1) / teams, h->track_grid));
@@ -1343,7 +1353,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                     c.xptr = h->d_xptr, c.cross = h->d_xcross, c.cur_w = h->d_curw, c.flx_w = h->d_flxw;
                     c.plane_surf_offset = h->d_plane_surf_offset, c.current = h->d_current, c.surface_flux = h->d_surfflux;
                     c.dsum = h->d_dsum, c.ssum = h->d_ssum, c.n_surf_plane = h->n_surf_plane, c.n_plane_total = h->n_plane;
-                    pick_chunk_kernel(tl.np, nw, tally)<<<cgrid, 32 * nw * teams, teams * chunk_warp_bytes(caps, tl.np),
+                    pick_chunk_kernel(tl.np, nw, tally)<<<cgrid, 32 * nw * teams, teams * chunk_warp_bytes(caps, tl.np, tl_tally),
                                                    h->stream>>>(c);
                 } else {
                     pick_warp_kernel(gl, tl.np, tally, cached)<<<grid, kWarpBlock, cached ? 0 : track_smem_bytes(h),

@@ -43,24 +43,27 @@ constexpr int kChunkMaxTeam  = 2;  // warps cooperating on one track
 
 // One (track, polar bundle) of the chunk kernel: everything a warp needs to start the track in ONE
 // dependent load (the boundary linkage of BoundaryCondition::update, boundary_condition.cpp:155-191,
-// is resolved at set-up). 96 bytes.
+// is resolved at set-up). 112 bytes.
 struct __align__(16) ChunkUnit {
     int32_t seg_begin; // first segment in the padded segment arrays (multiple of 4)
     int32_t nseg;
     int32_t cpos;      // position of the first (padded) segment inside the list's attenuation cache
-    int32_t pad;
+    int32_t cross_begin; // crossing lists of the track: forward list, sentinel, backward list, sentinel
     int32_t ang[4];    // sweep-angle indices of the bundle (octants 1-2)
     int32_t in_f[4];   // boundary slot the forward sweep starts from (per polar angle; plane-relative)
     int32_t in_b[4];   // ... the backward sweep
     int32_t out_f[4];  // where the forward exit flux goes: slot >= 0 copy, -(slot+1) write zero (vacuum),
     int32_t out_b[4];  // INT32_MIN leave alone (prescribed); ... backward exit flux
+    int32_t n_fw, n_bw; // entries of the forward / backward crossing list (sentinels not counted)
+    int32_t pad0, pad1;
 };
 
 // bytes of dynamic shared memory one warp needs for `caps` segments: attenuations [caps][P],
 // q-bar [caps], summed contributions [caps] (doubles), FSR ids [2][caps] (int32, double-buffered)
-__host__ __device__ inline size_t chunk_warp_bytes(int caps, int P)
+__host__ __device__ inline size_t chunk_warp_bytes(int caps, int P, bool tally = false)
 {
-    return (size_t)caps * ((size_t)(P + 2) * sizeof(double) + 2 * sizeof(int32_t));
+    // tally variants also stage the track's crossing lists: caps / 2 entries of 8 bytes
+    return (size_t)caps * ((size_t)(P + 2) * sizeof(double) + 2 * sizeof(int32_t) + (tally ? 4 : 0));
 }
 
 // 8-byte asynchronous copy global -> shared (LDGSTS): the scattered q-bar gather lands in shared
@@ -103,11 +106,21 @@ __device__ __forceinline__ void chunk_compose(const double *exb, const double *q
 #pragma unroll
     for (int p = 0; p < P; p++)
         A[p] = 1.0, Bf[p] = 0.0, Bb[p] = 0.0;
-#pragma unroll 2
+    if (lo >= hi)
+        return;
+    double ne[P], nq;
+    load_ex<P>(exb, lo, ne); // software pipeline: operands of segment k + 1 requested before segment k computes
+    nq = qb[lo];
     for (int k = lo; k < hi; k++) {
         double e[P];
-        load_ex<P>(exb, k, e);
-        const double q = qb[k];
+#pragma unroll
+        for (int p = 0; p < P; p++)
+            e[p] = ne[p];
+        const double q = nq;
+        if (k + 1 < hi) {
+            load_ex<P>(exb, k + 1, ne);
+            nq = qb[k + 1];
+        }
 #pragma unroll
         for (int p = 0; p < P; p++) {
             const double bq = q * (1.0 - e[p]);
@@ -153,13 +166,29 @@ template <int P>
 __device__ __forceinline__ void chunk_walk(const double *exb, const double *qb, double *ab, int lo, int hi,
                                            const double (&wt)[P], double (&psi_f)[P], double (&psi_b)[P])
 {
-    int kf = lo, kb = hi - 1;
-    for (; kf < kb; ++kf, --kb) { // first visit of both segments
+    const int len = hi - lo;
+    if (len <= 0)
+        return;
+    // software pipeline: the shared-memory operands of step j + 1 are requested before step j computes
+    double nf[P], nr[P], nqf, nqr;
+    load_ex<P>(exb, lo, nf);
+    load_ex<P>(exb, hi - 1, nr);
+    nqf = qb[lo], nqr = qb[hi - 1];
+    for (int j = 0; j < len; j++) {
+        const int kf = lo + j, kb = hi - 1 - j; // forward walk at kf, backward walk at kb
         double ef[P], er[P];
-        load_ex<P>(exb, kf, ef);
-        load_ex<P>(exb, kb, er);
-        const double qf = qb[kf], qr = qb[kb];
+#pragma unroll
+        for (int p = 0; p < P; p++)
+            ef[p] = nf[p], er[p] = nr[p];
+        const double qf = nqf, qr = nqr;
         double sf = 0.0, sr = 0.0;
+        if (kf > kb) // second visits: add to what the other direction left
+            sf = ab[kf], sr = ab[kb];
+        if (j + 1 < len) {
+            load_ex<P>(exb, kf + 1, nf);
+            load_ex<P>(exb, kb - 1, nr);
+            nqf = qb[kf + 1], nqr = qb[kb - 1];
+        }
 #pragma unroll
         for (int p = 0; p < P; p++) {
             const double df = (psi_f[p] - qf) * (1.0 - ef[p]);
@@ -169,43 +198,12 @@ __device__ __forceinline__ void chunk_walk(const double *exb, const double *qb, 
             sf = fma(df, wt[p], sf);
             sr = fma(dr, wt[p], sr);
         }
-        ab[kf] = sf;
-        ab[kb] = sr;
-    }
-    if (kf == kb) { // middle segment of an odd chunk: both directions at once
-        double em[P];
-        load_ex<P>(exb, kf, em);
-        const double qm = qb[kf];
-        double s = 0.0;
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-            const double df = (psi_f[p] - qm) * (1.0 - em[p]);
-            const double dr = (psi_b[p] - qm) * (1.0 - em[p]);
-            psi_f[p] -= df;
-            psi_b[p] -= dr;
-            s = fma(df, wt[p], s);
-            s = fma(dr, wt[p], s);
+        if (kf == kb) { // middle segment of an odd chunk: both directions at once
+            ab[kf] = sf + sr;
+        } else {
+            ab[kf] = sf;
+            ab[kb] = sr;
         }
-        ab[kf] = s;
-        ++kf, --kb;
-    }
-    for (; kf < hi; ++kf, --kb) { // second visits: add to what the other direction left
-        double ef[P], er[P];
-        load_ex<P>(exb, kf, ef);
-        load_ex<P>(exb, kb, er);
-        const double qf = qb[kf], qr = qb[kb];
-        double sf = ab[kf], sr = ab[kb];
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-            const double df = (psi_f[p] - qf) * (1.0 - ef[p]);
-            const double dr = (psi_b[p] - qr) * (1.0 - er[p]);
-            psi_f[p] -= df;
-            psi_b[p] -= dr;
-            sf = fma(df, wt[p], sf);
-            sr = fma(dr, wt[p], sr);
-        }
-        ab[kf] = sf;
-        ab[kb] = sr;
     }
 }
 
@@ -245,6 +243,8 @@ struct ChunkArgs {
 struct ChunkTallyCtx {
     const ChunkArgs *a;
     const int32_t *fb; // FSR ids of the staged block (plane-local)
+    const Cross *xl;   // crossing lists of the track (shared-memory copy when it fits, else global)
+    int n_fw, n_bw;
     int seg_begin, nseg, k_off; // track position of the staged block
     int plane, first_reg, grel, g;
     int ang[4];
@@ -278,8 +278,8 @@ __device__ __forceinline__ void chunk_walk_tally(const double *exb, const double
         double cs = 0.0, fsum = 0.0;
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            cs   = fma(psi[p], cw[p][norm], cs);
-            fsum = fma(psi[p], fw[p][norm], fsum);
+            cs   = fma(psi[p], norm ? cw[p][1] : cw[p][0], cs);
+            fsum = fma(psi[p], norm ? fw[p][1] : fw[p][0], fsum);
         }
         // forward adds, backward subtracts (moc_current_worker.hpp:230-231); the corrections worker also
         // subtracts the backward SURFACE FLUX (correction_worker.hpp:136-137, 194-195)
@@ -299,28 +299,25 @@ __device__ __forceinline__ void chunk_walk_tally(const double *exb, const double
         atomicAdd(&a.dsum[o], d);
     };
     const int nseg = c.nseg;
-    // first crossings at or after the chunk's first node, in either walk order
+    // first crossings at or after the chunk's first node, in either walk order (binary search in the lists)
     const int kt_lo = c.k_off + lo, kt_hi = c.k_off + hi; // track positions [kt_lo, kt_hi)
-    // (the lists are walked through a three-deep register queue so that the dependent global loads of the
-    // next crossings overlap the segments in between; the lists end in sentinels and the array is padded)
-    int ci_f = a.xptr[(c.seg_begin + (kt_lo & ~3)) >> 2].x;
-    int ci_b = a.xptr[(c.seg_begin + ((kt_hi - 1) & ~3)) >> 2].y;
-    Cross xf = a.cross[ci_f], xf1 = a.cross[ci_f + 1], xf2 = a.cross[ci_f + 2];
-    Cross xb = a.cross[ci_b], xb1 = a.cross[ci_b + 1], xb2 = a.cross[ci_b + 2];
-    auto next_f = [&]() {
-        xf = xf1, xf1 = xf2;
-        ++ci_f;
-        xf2 = a.cross[ci_f + 2];
+    const Cross *xfl = c.xl, *xbl = c.xl + c.n_fw + 1;
+    auto lower_bound = [](const Cross *l, int n, int node) {
+        int a0 = 0, a1 = n; // first index with l[i].node >= node (the sentinel at n has node INT32_MAX)
+        while (a0 < a1) {
+            const int m = (a0 + a1) >> 1;
+            if (l[m].node < node)
+                a0 = m + 1;
+            else
+                a1 = m;
+        }
+        return a0;
     };
-    auto next_b = [&]() {
-        xb = xb1, xb1 = xb2;
-        ++ci_b;
-        xb2 = a.cross[ci_b + 2];
-    };
-    while (xf.node < kt_lo)
-        next_f();
-    while (xb.node < nseg - kt_hi)
-        next_b();
+    int ci_f = lower_bound(xfl, c.n_fw, kt_lo);
+    int ci_b = lower_bound(xbl, c.n_bw, nseg - kt_hi);
+    Cross xf = xfl[ci_f], xb = xbl[ci_b];
+    auto next_f = [&]() { xf = xfl[++ci_f]; };
+    auto next_b = [&]() { xb = xbl[++ci_b]; };
     // ---- forward ----
     for (int k = lo; k < hi; k++) {
         const int kt = c.k_off + k; // forward flux at the node in front of segment kt
@@ -404,11 +401,12 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
     const int tl   = wl * 32 + lane; // lane within the team
     const bool leader = tl == 0;          // work counter, backward exit flux
     const bool loader = tl == T - 32;     // first lane of the team's last warp: issues the TMA copies
-    char *wbase    = reinterpret_cast<char *>(s_dyn) + (size_t)team * chunk_warp_bytes(caps, P);
+    char *wbase    = reinterpret_cast<char *>(s_dyn) + (size_t)team * chunk_warp_bytes(caps, P, TALLY != 0);
     double *exb    = reinterpret_cast<double *>(wbase);
     double *qb     = exb + (size_t)caps * P;
     double *ab     = qb + caps;
     int32_t *fbuf  = reinterpret_cast<int32_t *>(ab + caps); // two FSR-id buffers (plane-local ids)
+    Cross *xsm     = reinterpret_cast<Cross *>(fbuf + 2 * caps); // TALLY: the track's crossing lists (caps / 2 entries)
     uint64_t *bar  = &s_bar[3 * team];                       // [0], [1] FSR-id buffers, [2] attenuations
     auto team_sync = [&]() {
         if (NW == 1)
@@ -435,14 +433,14 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
     // ---- asynchronous two-level prefetch of a work item into its shared-memory slot ----
     // level 1: descriptor and plane info (addresses depend on the work index only)
     auto prefetch_unit = [&](uint32_t w, ChunkWork *k) {
-        if (wl == NW - 1 && lane < 8) {
+        if (wl == NW - 1 && lane < 9) {
             const uint32_t unit_id = w / per_unit;
             const uint32_t r       = w - unit_id * per_unit;
             const uint32_t ipl     = r / (uint32_t)a.g_count;
-            if (lane < 6)
+            if (lane < 7)
                 cp_async_16(reinterpret_cast<char *>(&k->u) + 16 * lane,
                             reinterpret_cast<const char *>(a.units + unit_id) + 16 * lane);
-            else if (lane == 6)
+            else if (lane == 7)
                 cp_async_8(&k->pinfo, a.pinfo + ipl);
             else
                 k->ipl = (int)ipl, k->grel = (int)(r - ipl * (uint32_t)a.g_count);
@@ -503,6 +501,14 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
 #pragma unroll 8
         for (int i = tl; i < n; i += T)
             cp_async_8(qb + i, qf + fb[i]);
+        if (TALLY != 0) { // crossing lists of the track (both sentinels included) when they fit
+            const int nx = k->u.n_fw + k->u.n_bw + 2;
+            if (nx <= caps / 2) {
+                const Cross *src = a.cross + k->u.cross_begin;
+                for (int i = tl; i < nx; i += T)
+                    cp_async_8(xsm + i, src + i);
+            }
+        }
     };
     auto wait_staged = [&]() {
         if (a.ex_mode == 0) {
@@ -578,6 +584,8 @@ __global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(con
         } else {
             ChunkTallyCtx c;
             c.a = &a, c.fb = fbuf + fi * caps;
+            c.n_fw = k->u.n_fw, c.n_bw = k->u.n_bw;
+            c.xl = (c.n_fw + c.n_bw + 2 <= caps / 2) ? xsm : a.cross + k->u.cross_begin;
             c.seg_begin = k->u.seg_begin, c.nseg = k->u.nseg, c.k_off = k_off;
             c.plane = k->pinfo.x, c.first_reg = k->pinfo.y, c.grel = k->grel, c.g = a.g_begin + k->grel;
 #pragma unroll
