@@ -1245,16 +1245,21 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         }
         // q-bar and tally reset (whole FSR range: cheap, keeps indexing simple)
         const int ss_grid = grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count);
-        if (h->kernel == MOCB200_KERNEL_ITEM)
+        // per-group sweeps fuse the flux update of inner i with the q-bar of inner i + 1 (see the end of the loop)
+        const bool fuse_q = group_major && !use_qbar && h->n_counters <= 256;
+        if (h->kernel == MOCB200_KERNEL_ITEM) {
             self_scatter_kernel<<<ss_grid, 256, 0, h->stream>>>(
                 h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_qbar,
                 h->d_tally, use_qbar ? 0 : 1);
-        else
+            h->stats.kernel_launches++;
+        } else if (inner == 0 || !fuse_q) {
             self_scatter_q_kernel<<<ss_grid, 256, 0, h->stream>>>(
                 h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_xstr,
                 h->d_qbar, group_major ? h->d_qg : h->d_qbar, cached ? nullptr : h->d_xq,
-                group_major ? h->d_tg : h->d_tally, group_major ? 1 : 0, use_qbar ? 0 : 1);
-        h->stats.kernel_launches++;
+                group_major ? h->d_tg : h->d_tally, group_major ? 1 : 0, use_qbar ? 0 : 1, h->d_counters,
+                h->n_counters <= 256 ? h->n_counters : 0);
+            h->stats.kernel_launches++;
+        }
         if (tally != MOCB200_TALLY_NONE) {
             zero_groups_kernel<<<grid_for((int64_t)h->n_surf * g_count, 256, h->sm_count), 256, 0, h->stream>>>(
                 h->n_surf, h->GP, g_begin, g_count, h->d_current);
@@ -1262,7 +1267,8 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 h->n_surf, h->GP, g_begin, g_count, h->d_surfflux);
             h->stats.kernel_launches += 2;
         }
-        CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * h->n_counters, h->stream));
+        if (h->kernel == MOCB200_KERNEL_ITEM || h->n_counters > 256)
+            CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * h->n_counters, h->stream));
         if (last)
             CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
         if (h->timing) {
@@ -1390,9 +1396,14 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         }
         if (jacobi)
             h->bc_cur = 1 - h->bc_cur;
-        finalize_flux_q_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
-            h->n_reg, h->GP, g_begin, g_count, group_major ? h->d_tg : h->d_tally, h->d_xstr, h->d_vol, h->d_qbar,
-            h->d_flux, h->reg_lo, h->reg_hi, group_major ? 1 : 0);
+        if (fuse_q && !last)
+            finalize_next_q_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
+                h->n_reg, h->GP, g_begin, g_count, h->d_tg, h->d_xstr, h->d_vol, h->d_qbar, h->d_flux, h->reg_lo,
+                h->reg_hi, h->d_src, h->d_xs_self, h->d_xstr_src, h->d_qg, h->d_counters, h->n_counters);
+        else
+            finalize_flux_q_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
+                h->n_reg, h->GP, g_begin, g_count, group_major ? h->d_tg : h->d_tally, h->d_xstr, h->d_vol, h->d_qbar,
+                h->d_flux, h->reg_lo, h->reg_hi, group_major ? 1 : 0);
         h->stats.kernel_launches++;
         CUDA_TRY(h, cudaGetLastError());
     }

@@ -726,8 +726,11 @@ __global__ void self_scatter_q_kernel(int n_reg, int GP, int g_begin, int g_coun
                                       const double *__restrict__ flux, const double *__restrict__ xs_self,
                                       const double *__restrict__ xstr_src, const double *__restrict__ xstr,
                                       double *qbar, double *q_out, double2 *__restrict__ xq,
-                                      double *__restrict__ tally_out, int group_major, int compute_q)
+                                      double *__restrict__ tally_out, int group_major, int compute_q,
+                                      uint32_t *__restrict__ counters, int n_counters)
 {
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_counters) // work counters of the sweep kernels that follow
+        counters[threadIdx.x] = 0u;
     const int64_t n = (int64_t)n_reg * g_count;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int r, gi;
@@ -778,6 +781,36 @@ __global__ void finalize_flux_q_kernel(int n_reg, int GP, int g_begin, int g_cou
         const size_t o  = (size_t)r * GP + g;
         const size_t oo = group_major ? (size_t)gi * n_reg + r : o;
         flux[o] = __dadd_rn(__ddiv_rn(tally[oo], __dmul_rn(xstr[o], vol[r])), __dmul_rn(qbar[o], kFPi));
+    }
+}
+
+// finalize_flux_q_kernel of inner iteration i fused with self_scatter_q_kernel of iteration i + 1 (group-major
+// q-bar / tally of the per-group sweeps): flux = tally/(xstr*vol) + qbar*4pi; qbar' = (src + flux*xs_self) /
+// (xstr_src*4pi); tally = 0; work counters = 0. Same non-contracted arithmetic as the two kernels.
+__global__ void finalize_next_q_kernel(int n_reg, int GP, int g_begin, int g_count, double *__restrict__ tally,
+                                       const double *__restrict__ xstr, const double *__restrict__ vol,
+                                       double *__restrict__ qbar, double *__restrict__ flux, int reg_lo, int reg_hi,
+                                       const double *__restrict__ src, const double *__restrict__ xs_self,
+                                       const double *__restrict__ xstr_src, double *__restrict__ q_out,
+                                       uint32_t *__restrict__ counters, int n_counters)
+{
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_counters)
+        counters[threadIdx.x] = 0u;
+    const int nr    = reg_hi - reg_lo;
+    const int64_t n = (int64_t)nr * g_count;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int gi    = (int)(i / nr);
+        const int r     = reg_lo + (int)(i - (int64_t)gi * nr);
+        const int g     = g_begin + gi;
+        const size_t o  = (size_t)r * GP + g;
+        const size_t oo = (size_t)gi * n_reg + r;
+        const double f  = __dadd_rn(__ddiv_rn(tally[oo], __dmul_rn(xstr[o], vol[r])), __dmul_rn(qbar[o], kFPi));
+        flux[o]         = f;
+        const double r_fpi_tr = __ddiv_rn(1.0, __dmul_rn(xstr_src[o], kFPi));
+        const double q        = __dmul_rn(__dadd_rn(src[o], __dmul_rn(f, xs_self[o])), r_fpi_tr);
+        qbar[o]   = q;
+        q_out[oo] = q;
+        tally[oo] = 0.0;
     }
 }
 
