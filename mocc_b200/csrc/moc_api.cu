@@ -842,7 +842,7 @@ template <int NW, int TALLY> ChunkFn pick_chunk_np(int np)
 
 ChunkFn pick_chunk_kernel(int np, int nw, int tally)
 {
-    switch ((nw == 2 ? 3 : 0) + tally) {
+    switch ((nw - 1) * 3 + tally) {
     case 0: return pick_chunk_np<1, 0>(np);
     case 1: return pick_chunk_np<1, 1>(np);
     case 2: return pick_chunk_np<1, 2>(np);
@@ -853,7 +853,7 @@ ChunkFn pick_chunk_kernel(int np, int nw, int tally)
     return nullptr;
 }
 
-constexpr int kChunkSmemBudget = 232448 - 12288; // opt-in dynamic shared memory per CTA minus the static part
+constexpr int kChunkSmemBudget = 232448 - 14336; // opt-in dynamic shared memory per CTA minus the static part
 
 // launch geometry of the chunk kernel for a list: segments a team stages at once, warps per team,
 // teams per CTA
@@ -868,9 +868,10 @@ void chunk_geometry(int max_nseg, int np, int cap_opt, bool tally, int *caps, in
     *caps  = c;
     *nw    = c >= 256 ? 2 : 1;
     static const char *force_nw = getenv("MOCB200_CHUNK_NW"); // tuning hook: warps per track (1 or 2)
-    if (force_nw && (force_nw[0] == '1' || force_nw[0] == '2'))
+    if (force_nw && force_nw[0] >= '1' && force_nw[0] <= '0' + kChunkMaxTeam)
         *nw = force_nw[0] - '0';
-    *teams = std::max(1, std::min<int>(kChunkMaxWarps / *nw, kChunkSmemBudget / (int)chunk_warp_bytes(c, np, tally)));
+    *teams = std::max(1, std::min<int>(std::min(chunk_max_warps(*nw) / *nw, kChunkMaxTeams),
+                                       kChunkSmemBudget / (int)chunk_warp_bytes(c, np, tally)));
 }
 
 int track_smem_bytes(const mocb200_sweeper *h)
@@ -1343,7 +1344,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                     chunk_geometry(tl.max_nseg, tl.np, h->opt.chunk_cap, tl_tally, &caps, &nw, &teams);
                     if (h->opt.chunk_cap < 0) // test hook: negative cap = that cap with two-warp teams
                         chunk_geometry(tl.max_nseg, tl.np, -h->opt.chunk_cap, tl_tally, &caps, &nw, &teams), nw = 2,
-                            teams = std::min(teams, kChunkMaxWarps / 2);
+                            teams = std::min(teams, chunk_max_warps(2) / 2);
                     const int cgrid =
                         (int)std::max<int64_t>(1, std::min<int64_t>((warps + teams - 1) / teams, h->track_grid));
                     ChunkArgs c{};

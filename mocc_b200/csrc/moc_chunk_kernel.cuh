@@ -38,8 +38,14 @@
 
 namespace mocb200 {
 
-constexpr int kChunkMaxWarps = 14; // 448 threads: up to 146 registers per thread (occupancy is shared-memory bound)
-constexpr int kChunkMaxTeam  = 2;  // warps cooperating on one track
+constexpr int kChunkMaxTeam  = 2;  // warps cooperating on one track (3 and 4 measured slower: profiles/r1/tuning.md)
+constexpr int kChunkMaxTeams = 14; // teams per CTA
+// warps per CTA: the register budget per thread follows (1-2 warps per track: 448 threads, 146 registers;
+// 3: 672 threads, 97 registers; 4: 896 threads, 73 registers)
+__host__ __device__ constexpr int chunk_max_warps(int nw)
+{
+    return nw <= 2 ? 14 : (nw == 3 ? 21 : 28);
+}
 
 // One (track, polar bundle) of the chunk kernel: everything a warp needs to start the track in ONE
 // dependent load (the boundary linkage of BoundaryCondition::update, boundary_condition.cpp:155-191,
@@ -385,14 +391,14 @@ struct __align__(16) ChunkWork {
 
 // NW warps ("team") cooperate on one track: 32 NW lanes, each owning one contiguous chunk.
 template <int P, int NW, int TALLY>
-__global__ void __launch_bounds__(32 * kChunkMaxWarps, 1) sweep_chunk_kernel(const ChunkArgs a)
+__global__ void __launch_bounds__(32 * chunk_max_warps(NW), 1) sweep_chunk_kernel(const ChunkArgs a)
 {
     constexpr int T = 32 * NW; // lanes of a team
     extern __shared__ __align__(16) double s_dyn[];
-    __shared__ uint64_t s_bar[3 * kChunkMaxWarps];
-    __shared__ double s_tot[kChunkMaxWarps][kChunkMaxTeam][4][4]; // per team, per warp: Af, Bf, Ab, Bb of the warp's lanes
-    __shared__ uint32_t s_w[2 * kChunkMaxWarps];
-    __shared__ ChunkWork s_work[kChunkMaxWarps][2];
+    __shared__ uint64_t s_bar[3 * kChunkMaxTeams];
+    __shared__ double s_tot[kChunkMaxTeams][kChunkMaxTeam][4][4]; // per team, per warp: Af, Bf, Ab, Bb of the warp's lanes
+    __shared__ uint32_t s_w[2 * kChunkMaxTeams];
+    __shared__ ChunkWork s_work[kChunkMaxTeams][2];
 
     const int caps = a.caps;
     const int lane = threadIdx.x & 31;
