@@ -218,8 +218,14 @@ def main():
             for g in range(G):
                 sw.sweep(g, 1, n_inner=n_inner, tally_mode=TALLY_CURRENT)
 
-    flux_h = np.ones((G, n_reg))
-    bc_h = [bc0.copy() for _ in range(n_plane)]
+    # host buffers of the e2e path live in page-locked memory (the C ABI then copies straight from / into them)
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = a
+        return t.numpy()
+    src = pinned(src)
+    flux_h = pinned(np.ones((G, n_reg)))
+    bc_h = [pinned(bc0) for _ in range(n_plane)]
     h2d = d2h = 0
 
     def step_e2e(count=False):

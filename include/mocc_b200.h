@@ -213,7 +213,9 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
  *                      (boundary NULL or entry NULL = keep); planes outside this handle's range are ignored.
  *                      Returns once the host arrays may be reused; the copy is stream-ordered before the sweep.
  *   get_sweep_results: flux[n_reg] (only this handle's FSR range is written), boundary[ip] as above,
- *                      current/surface_flux[n_surf] as mocb200_get_coarse (both NULL = skip). Synchronises. */
+ *                      current/surface_flux[n_surf] as mocb200_get_coarse (both NULL = skip). Synchronises.
+ * Page-locked host arrays (cudaHostAlloc / cudaHostRegister) are copied to / from directly, without the staging
+ * memcpy; such input arrays must stay unmodified until the next synchronising call on the handle. */
 int mocb200_set_sweep_inputs(mocb200_sweeper *h, int group, const double *source, const double *flux,
                              const double *const *boundary);
 int mocb200_get_sweep_results(mocb200_sweeper *h, int group, double *flux, double *const *boundary, double *current,

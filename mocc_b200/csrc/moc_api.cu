@@ -879,6 +879,17 @@ int track_smem_bytes(const mocb200_sweeper *h)
     return (((h->exp_n + 2) * (int)sizeof(double)) + 15) & ~15;
 }
 
+// page-locked host memory (cudaHostAlloc / cudaHostRegister) can be the source or target of a DMA directly
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int check_groups(mocb200_sweeper *h, int g_begin, int g_count)
 {
     if (!h)
@@ -1424,30 +1435,54 @@ int mocb200_set_sweep_inputs(mocb200_sweeper *h, int group, const double *source
     }
     const size_t nr = (size_t)h->n_reg, nb = (size_t)h->bcpg;
     size_t off = 0;
+    bool staged = false;
+    // pageable arrays are packed into the pinned staging buffer (one copy for all of them, flushed at the
+    // end); page-locked arrays are copied straight from where they are (no host memcpy)
+    size_t run_begin = 0;
+    auto flush_staged = [&](size_t end) -> int {
+        if (end > run_begin) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_in + run_begin, h->h_in + run_begin, (end - run_begin) * sizeof(double),
+                                        cudaMemcpyHostToDevice, h->stream));
+            staged = true;
+        }
+        return MOCB200_OK;
+    };
+    auto put = [&](const double *src, size_t n) -> int {
+        if (is_pinned(src)) {
+            int rc2 = flush_staged(off);
+            if (rc2)
+                return rc2;
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_in + off, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            run_begin = off + n;
+        } else {
+            std::memcpy(h->h_in + off, src, n * sizeof(double));
+        }
+        off += n;
+        return MOCB200_OK;
+    };
     const size_t o_src = off;
-    if (source) {
-        std::memcpy(h->h_in + off, source, nr * sizeof(double));
-        off += nr;
-    }
+    if (source && (rc = put(source, nr)))
+        return rc;
     const size_t o_flux = off;
-    if (flux) {
-        std::memcpy(h->h_in + off, flux, nr * sizeof(double));
-        off += nr;
-    }
+    if (flux && (rc = put(flux, nr)))
+        return rc;
     const size_t o_bc = off;
     std::vector<int> bc_planes;
     for (int ip = h->plane_begin; boundary && ip < h->plane_end; ip++) {
         if (!boundary[ip])
             continue;
-        std::memcpy(h->h_in + off, boundary[ip], nb * sizeof(double));
-        off += nb;
+        if ((rc = put(boundary[ip], nb)))
+            return rc;
         bc_planes.push_back(ip);
     }
     if (off == 0)
         return MOCB200_OK;
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_in, h->h_in, off * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaEventRecord(h->ev_in, h->stream));
-    h->ev_in_pending = true;
+    if ((rc = flush_staged(off)))
+        return rc;
+    if (staged) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_in, h->stream));
+        h->ev_in_pending = true;
+    }
     auto scatter = [&](const double *cols, int64_t n, double *dst) {
         scatter_columns_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, h->stream>>>(n, h->GP, group, 1, cols, dst);
         h->stats.kernel_launches++;
@@ -1504,16 +1539,34 @@ int mocb200_get_sweep_results(mocb200_sweeper *h, int group, double *flux, doubl
     if (off == 0)
         return MOCB200_OK;
     CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, off * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    // page-locked targets receive their part directly; the rest goes through the pinned staging buffer
+    struct Piece {
+        double *dst;
+        size_t off, n;
+        bool direct;
+    };
+    std::vector<Piece> pieces;
     if (flux)
-        std::memcpy(flux + h->reg_lo, h->h_out + o_flux, nr * sizeof(double));
+        pieces.push_back({flux + h->reg_lo, o_flux, nr, is_pinned(flux)});
     for (size_t i = 0; i < bc_planes.size(); i++)
-        std::memcpy(boundary[bc_planes[i]], h->h_out + o_bc + i * nb, nb * sizeof(double));
+        pieces.push_back({boundary[bc_planes[i]], o_bc + i * nb, nb, is_pinned(boundary[bc_planes[i]])});
     if (current) {
-        std::memcpy(current, h->h_out + o_cur, ns * sizeof(double));
-        std::memcpy(surface_flux, h->h_out + o_cur + ns, ns * sizeof(double));
+        pieces.push_back({current, o_cur, ns, is_pinned(current)});
+        pieces.push_back({surface_flux, o_cur + ns, ns, is_pinned(surface_flux)});
     }
+    bool any_staged = false;
+    for (const Piece &pc : pieces) {
+        if (pc.direct)
+            CUDA_TRY(h, cudaMemcpyAsync(pc.dst, h->d_out + pc.off, pc.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        else
+            any_staged = true;
+    }
+    if (any_staged) // one copy for every staged piece (the direct ones are copied twice: simpler than splitting runs)
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, off * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (const Piece &pc : pieces)
+        if (!pc.direct)
+            std::memcpy(pc.dst, h->h_out + pc.off, pc.n * sizeof(double));
     return MOCB200_OK;
 }
 

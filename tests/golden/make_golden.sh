@@ -49,3 +49,21 @@ for c in mini2d mini2d3d 3x3; do
     tail -1 "$WORK/$c.solve.log"
     (cd "$ROOT" && python_pack "$WORK/$c.arrays" "$HERE/${c}_solve_ref.arrays.gz")
 done
+
+# C5G7 3-D (BASELINE.json config 4), FIRST OUTER ONLY of the 2D3D solve with the reference CPU sweepers, one thread.
+# (From the second outer on the reference itself diverges on this input: profiles/r1/c5g7_3d.md.) Compact golden:
+# k, every 97th flux entry, flux sum, pin powers.
+python "$ROOT/tools/make_c5g7_3d.py" "$ROOT/mocc_b200/bin/inputs/c5g7_2d.xml" "$WORK/c5g7_3d.xml" --max-iter 1
+cp "$ROOT/mocc_b200/bin/inputs/c5g7.xsl" "$WORK/"
+(cd "$WORK" && OMP_NUM_THREADS=1 "$SOLVE" c5g7_3d.xml "$WORK/c5g7_3d.arrays" > "$WORK/c5g7_3d.solve.log" 2>&1) || { tail -5 "$WORK/c5g7_3d.solve.log"; exit 1; }
+(cd "$ROOT" && python - "$WORK/c5g7_3d.arrays" "$HERE/c5g7_3d_outer1_ref.arrays.gz" <<'PY'
+import sys
+import numpy as np
+from mocc_b200 import load_arrays, save_arrays
+a = load_arrays(sys.argv[1])
+flux = a["flux"]
+save_arrays(sys.argv[2], {"k_history": a["k_history"], "flux_sample": np.ascontiguousarray(flux.reshape(-1)[::97]),
+                          "flux_stride": np.array([97], dtype=np.int32), "flux_shape": np.array(flux.shape, dtype=np.int64),
+                          "flux_sum": np.array([flux.sum()]), "pin_powers": a["pin_powers"]})
+PY
+)
