@@ -303,3 +303,61 @@ def test_errors_are_reported():
     with pytest.raises(RuntimeError, match="group range"):
         sw.set_qbar(99, np.zeros(sw.n_reg))
     sw.close()
+
+
+@pytest.fixture(scope="module")
+def c5g7_2d_flat():
+    """BASELINE.json config 2 at full size, flattened on the box by the plugin's own set-up code."""
+    import bench
+    from mocc_b200 import load_arrays
+    return load_arrays(bench.workload_files())
+
+
+@pytest.mark.parametrize("kernel,jacobi", [(0, False), (0, True), (3, False)])
+def test_full_size_c5g7_2d_sweeps_match_oracle(c5g7_2d_flat, kernel, jacobi):
+    """Full-size parity (18.2 M reference segments per group sweep): every group, with and without the coarse-current
+    tally, two inners with self scatter on the device, against the C oracle on the same seeded inputs."""
+    flat = c5g7_2d_flat
+    G, n_reg, bcpg = (int(flat[k][0]) for k in ("n_group", "n_reg", "bc_per_group"))
+    rng = np.random.default_rng(2025)
+    sw = _sweeper(flat, boundary_update=1 if jacobi else 0, kernel=kernel)
+    assert sw.stats()["kernel"] == (4 if kernel == 0 else kernel)
+    sw.set_xs(0, flat["xs_tr"], xstr_src=flat["xs_tr"], xs_self=flat["xs_self"])
+    xy = _xy_mask(flat)
+    area = flat["surf_area"]
+    for g in range(G):
+        tally = g % 2
+        qbar = rng.uniform(0.05, 1.0, size=n_reg)
+        bc = rng.uniform(0.0, 0.3, size=(1, bcpg))
+        sw.set_qbar(g, qbar)
+        sw.set_boundary(0, g, bc[0])
+        sw.sweep(g, 1, n_inner=1, tally_mode=tally, use_qbar=True)
+        f_o, bc_o, cur_o, sf_o = oracle_sweep1g(flat, flat["xs_tr"][g], qbar, bc, gs_boundary=not jacobi, tally_mode=tally)
+        _close(sw.get_flux(g, 1)[0], f_o)
+        _close(sw.get_boundary(0, g, 1)[0], bc_o[0])
+        if tally:
+            cur, sf = sw.get_coarse(g)
+            _close(cur[xy] / area[xy], cur_o[xy], atol=1e-13)
+            _close(sf[xy] / area[xy], sf_o[xy], atol=1e-13)
+    sw.close()
+
+
+def test_full_size_sweep_is_linear_in_source_and_boundary_flux(c5g7_2d_flat):
+    """Size-independent property: for fixed cross sections the sweep is linear in (q-bar, incoming flux)."""
+    flat = c5g7_2d_flat
+    n_reg, bcpg = int(flat["n_reg"][0]), int(flat["bc_per_group"][0])
+    rng = np.random.default_rng(7)
+    g = 5
+    sw = _sweeper(flat, boundary_update=0)
+    sw.set_xs(0, flat["xs_tr"], xstr_src=flat["xs_tr"], xs_self=flat["xs_self"])
+    q = [rng.uniform(0.05, 1.0, size=n_reg) for _ in range(2)]
+    b = [rng.uniform(0.0, 0.3, size=bcpg) for _ in range(2)]
+    out = []
+    for qq, bb in ((q[0], b[0]), (q[1], b[1]), (2.0 * q[0] + 0.5 * q[1], 2.0 * b[0] + 0.5 * b[1])):
+        sw.set_qbar(g, qq)
+        sw.set_boundary(0, g, bb)
+        sw.sweep(g, 1, n_inner=1, tally_mode=1, use_qbar=True)
+        out.append((sw.get_flux(g, 1)[0], sw.get_boundary(0, g, 1)[0]) + sw.get_coarse(g))
+    for x0, x1, x2 in zip(*out):
+        _close(x2, 2.0 * x0 + 0.5 * x1, rtol=1e-10, atol=1e-12)
+    sw.close()
