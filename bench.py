@@ -51,10 +51,21 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def workload_files():
+WORKLOADS = {
+    # BASELINE.json configs[1]: the reference's example as shipped (the headline workload)
+    "c5g7_2d": ("C5G7 2-D (examples/c5g7_2d.xml): 7 groups, cg 8x2, spacing 0.05, n_inner 10, coarse-current tally on "
+                "the last inner", []),
+    # BASELINE.json configs[2] / SURVEY.md 8(d) "dense-A": same file, denser quadrature and rays (~x10 segments)
+    "dense_a": ("C5G7 2-D dense-A (examples/c5g7_2d.xml with cg 16x4, spacing 0.02): 7 groups, n_inner 10, "
+                "coarse-current tally on the last inner",
+                ["solver/ang_quad@n_azimuthal=16", "solver/ang_quad@n_polar=4", "solver/sweeper/rays@spacing=0.02"]),
+}
+
+
+def workload_files(name="c5g7_2d"):
     """Flatten examples/c5g7_2d.xml with the plugin's own setup code (mocc_flatten)."""
     os.makedirs(CACHE, exist_ok=True)
-    flat = os.path.join(CACHE, "c5g7_2d.mocflat")
+    flat = os.path.join(CACHE, f"{name}.mocflat")
     if not os.path.exists(flat):
         tool = os.path.join(BIN, "mocc_flatten")
         inputs = os.path.join(BIN, "inputs")
@@ -62,7 +73,8 @@ def workload_files():
             raise RuntimeError("mocc_b200/bin/mocc_flatten missing: run __graft_entry__.build() where the "
                                "reference sources are available")
         tmp = flat + f".tmp{os.getpid()}"
-        subprocess.check_call([tool, "c5g7_2d.xml", tmp, "--xs"], cwd=inputs, stdout=subprocess.DEVNULL)
+        sets = [x for s in WORKLOADS[name][1] for x in ("--set", s)]
+        subprocess.check_call([tool, "c5g7_2d.xml", tmp, "--xs"] + sets, cwd=inputs, stdout=subprocess.DEVNULL)
         os.replace(tmp, flat)
     return flat
 
@@ -161,6 +173,8 @@ def main():
     ap.add_argument("--boundary", default="gs", choices=["gs", "jacobi"])
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c5g7_2d", choices=sorted(WORKLOADS))
+    ap.add_argument("--max-polar", type=int, default=0, help="polar angles bundled per track (0 = library default, 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -187,9 +201,9 @@ def main():
         torch.cuda.synchronize()
 
     if rank == 0:
-        flat_path = workload_files()
+        flat_path = workload_files(args.workload)
     barrier()
-    flat_path = workload_files()
+    flat_path = workload_files(args.workload)
     arr = load_arrays(flat_path)
     G, n_reg, n_plane = (int(arr[k][0]) for k in ("n_group", "n_reg", "n_plane"))
     S = int(arr["n_seg_reference"][0])
@@ -198,7 +212,7 @@ def main():
     gs = args.boundary == "gs"
     src = synthetic_source(arr, G, n_reg)
 
-    sw = Sweeper(arr, device=local, boundary_update=0 if gs else 1, kernel=args.kernel)
+    sw = Sweeper(arr, device=local, boundary_update=0 if gs else 1, kernel=args.kernel, max_polar=args.max_polar)
     # a dedicated non-default stream: the C ABI treats a NULL stream as "use the handle's own", and
     # torch events only see work on the stream they are recorded on
     stream = torch.cuda.Stream()
@@ -284,13 +298,13 @@ def main():
     # shares geometry between the polar copies; its own compulsory bytes are reported beside it.
     n_useg = int(arr["seg_len"].size)
     n_ray = int(arr["n_ray_reference"][0])
-    bytes_contract = BYTES_PER_UPDATE * 2.0 * S if args.mode == "pergroup" else \
+    bytes_contract = BYTES_PER_UPDATE * 2.0 * S if (args.mode == "pergroup" and args.workload == "c5g7_2d") else \
         12.0 * S + groups_per_call * (24.0 * n_reg + 32.0 * n_ray)
     bytes_resident = 12.0 * n_useg + groups_per_call * (24.0 * n_reg + 32.0 * n_ray)
     achieved = bytes_contract / (sweep_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.workload == "c5g7_2d":
         traffic = json.load(open(tp)).get(args.mode)
 
     # ---- end to end through the C ABI with host buffers ----
@@ -308,7 +322,7 @@ def main():
 
     # ---- reference CPU sweep on this box's host cores (rank 0, N = 1): one step of the same workload ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_TOOL):
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "c5g7_2d" and os.path.exists(REF_TOOL):
         cores = os.cpu_count() or 1
         env = dict(os.environ, OMP_NUM_THREADS=str(cores))
         out = subprocess.run([REF_TOOL, "time", "c5g7_2d.xml", "--cmfd", "--sweeps", "1", "--warmup", "0"],
@@ -335,13 +349,12 @@ def main():
             "vs_baseline": None, "dtype": "f64",
             "data": "examples/c5g7_2d.xml geometry and cross sections (flattened on the box); synthetic fixed "
                     "source (fission + in-scatter of a flat unit flux)",
-            "config": {"workload": "C5G7 2-D (examples/c5g7_2d.xml): 7 groups, cg 8x2, spacing 0.05, n_inner 10, "
-                                   "coarse-current tally on the last inner" +
+            "config": {"workload": WORKLOADS[args.workload][0] +
                                    (f"; {world} axial planes, one per GPU" if world > 1 else ""),
                        "mode": args.mode, "boundary_update": args.boundary, "segments": S, "resident_segments": n_useg,
                        "n_reg": n_reg, "groups": G, "n_inner": n_inner, "updates_per_step": updates_step,
                        "l2": "256 MB flush write between timed steps; device-resident inputs 450 MB > 126 MB L2",
-                       "kernel": kname, "bundled_segments": int(st["swept_segments"])},
+                       "kernel": kname, "bundled_segments": int(st["swept_segments"]), "max_polar": args.max_polar or 2},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(ln.item()),
             "clocks": clocks,

@@ -98,6 +98,7 @@ struct mocb200_sweeper {
     double *d_qg = nullptr, *d_tg = nullptr; // group-major q-bar / tally [G][n_reg]
     // 2D3D correction factors
     bool have_corr = false;
+    std::string corr_why; // why MOCB200_TALLY_CORRECTIONS is unavailable
     std::vector<bool> have_sn_xs;
     int n_cell_plane = 0, n_geom = 0;
     int32_t *d_all_planes = nullptr; // macroplanes of this handle
@@ -612,7 +613,11 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     // ---- 2D3D correction-factor tables ----
     h->n_cell_plane = p.n_cell_plane, h->n_geom = p.n_geom;
     h->have_sn_xs.assign(p.n_group, false);
-    if (p.ang_area_x && p.ang_area_y && p.ang_ox && p.cell_dx && p.cell_dy) {
+    // A geometry whose ray data attribute one FSR to two coarse cells (rays through cell corners at very fine
+    // spacings do) cannot use the per-FSR form of the correction sums: the handle then works for everything
+    // except MOCB200_TALLY_CORRECTIONS, which reports why.
+    constexpr int kCorrUnavailable = -1000;
+    auto build_corr_tables = [&]() -> int {
         int rc3;
         // FSRs of every unique plane, their coarse cell (as the ray data attributes segments to cells,
         // correction_worker.hpp:145-162) and the path length of every geometry class through every FSR
@@ -644,8 +649,10 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                         if (s_fw != 7) {
                             for (int i = 0; i < n_fw; i++, iseg++) {
                                 int32_t &fc = fsr_cell[uniq_reg_begin[u] + p.seg_fsr[s0 + iseg]];
-                                if (fc >= 0 && fc != cell)
-                                    return fail(h, MOCB200_ERR_INVALID, "FSR attributed to two coarse cells");
+                                if (fc >= 0 && fc != cell) {
+                                    h->corr_why = "the ray data attribute an FSR to two coarse cells";
+                                    return kCorrUnavailable;
+                                }
                                 fc = cell;
                             }
                         }
@@ -662,8 +669,10 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
             int32_t *cb = cell_fsr_begin.data() + (size_t)u * (p.n_cell_plane + 1);
             for (int r = 0; r < nreg_u[u]; r++) {
                 const int c = fsr_cell[uniq_reg_begin[u] + r];
-                if (c < 0 || c >= p.n_cell_plane)
-                    return fail(h, MOCB200_ERR_INVALID, "FSR %d of unique plane %d is crossed by no ray", r, u);
+                if (c < 0 || c >= p.n_cell_plane) {
+                    h->corr_why = "an FSR is crossed by no ray";
+                    return kCorrUnavailable;
+                }
                 cb[c + 1]++;
             }
             for (int c = 0; c < p.n_cell_plane; c++)
@@ -694,6 +703,14 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
             return rc3;
         CUDA_TRY(h, cudaMemset(h->d_sn_xs, 0, nsx * sizeof(double)));
         h->have_corr = true;
+        return MOCB200_OK;
+    };
+    if (p.ang_area_x && p.ang_area_y && p.ang_ox && p.cell_dx && p.cell_dy) {
+        const int rc3 = build_corr_tables();
+        if (rc3 != MOCB200_OK && rc3 != kCorrUnavailable)
+            return rc3;
+    } else {
+        h->corr_why = "the problem was created without the 2D3D correction tables";
     }
 
     // ---- uploads ----
@@ -1166,7 +1183,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         if (h->kernel == MOCB200_KERNEL_ITEM)
             return fail(h, MOCB200_ERR_INVALID, "the item kernel has no correction-factor tally");
         if (!h->have_corr)
-            return fail(h, MOCB200_ERR_STATE, "problem was created without the 2D3D correction tables");
+            return fail(h, MOCB200_ERR_STATE, "2D3D correction factors unavailable: %s", h->corr_why.c_str());
         for (int g = g_begin; g < g_begin + g_count; g++)
             if (!h->have_sn_xs[g])
                 return fail(h, MOCB200_ERR_STATE, "mocb200_set_sn_xs has not been called for group %d", g);
