@@ -40,6 +40,10 @@ namespace mocb200 {
 
 constexpr int kChunkMaxTeam  = 2;  // warps cooperating on one track (3 and 4 measured slower: profiles/r1/tuning.md)
 constexpr int kChunkMaxTeams = 14; // teams per CTA
+#ifndef MOCB200_CHUNK_ODD_L
+#define MOCB200_CHUNK_ODD_L 1
+#endif
+constexpr int kChunkOddL = MOCB200_CHUNK_ODD_L; // 1: odd chunk length (conflict-free shared-memory strides)
 // warps per CTA: the register budget per thread follows (1-2 warps per track: 448 threads, 146 registers;
 // 3: 672 threads, 97 registers; 4: 896 threads, 73 registers)
 __host__ __device__ constexpr int chunk_max_warps(int nw)
@@ -536,7 +540,7 @@ __global__ void __launch_bounds__(32 * chunk_max_warps(NW), 1) sweep_chunk_kerne
     // (valid in the last lane of the team) and the backward flux leaving it (valid in team lane 0).
     auto block = [&](int n, int k_off, int fi, const ChunkWork *k, const double (&wt)[P], const double (&cf)[P],
                      const double (&eb)[P], double (&out_fwd)[P], double (&out_bwd)[P]) {
-        const int L  = ((n + T - 1) / T) | 1;
+        const int L  = ((n + T - 1) / T) | kChunkOddL;
         const int lo = min(tl * L, n), hi = min(lo + L, n);
         double A[P], Af[P], Bf[P], Ab[P], Bb[P];
         chunk_compose<P>(exb, qb, lo, hi, A, Bf, Bb);
@@ -694,7 +698,7 @@ __global__ void __launch_bounds__(32 * chunk_max_warps(NW), 1) sweep_chunk_kerne
                 issue_ex(cur, sb * caps, n);
                 gather_q(fi, cur, n);
                 wait_staged();
-                const int L  = ((n + T - 1) / T) | 1;
+                const int L  = ((n + T - 1) / T) | kChunkOddL;
                 const int lo = min(tl * L, n), hi = min(lo + L, n);
                 if (leader) {
 #pragma unroll
