@@ -361,3 +361,39 @@ def test_full_size_sweep_is_linear_in_source_and_boundary_flux(c5g7_2d_flat):
     for x0, x1, x2 in zip(*out):
         _close(x2, 2.0 * x0 + 0.5 * x1, rtol=1e-10, atol=1e-12)
     sw.close()
+
+
+@pytest.mark.parametrize("case", ["mini2d_gs", "mini3d_gs"])
+@pytest.mark.parametrize("n_inner", [1, 3])
+def test_two_groups_per_call_on_the_chunk_kernel(case, n_inner):
+    """g_count = 2 keeps one group per warp (chunk kernel, group-major q-bar / tally): equals two single-group calls."""
+    flat, gold = load_case(case)
+    G, n_reg, n_plane = (int(flat[k][0]) for k in ("n_group", "n_reg", "n_plane"))
+    bcpg = int(flat["bc_per_group"][0])
+    rng = np.random.default_rng(5)
+    xstr = np.stack([gold[f"xs_tr_{g}"] for g in range(G)])
+    xself = np.stack([gold[f"xs_self_{g}"] for g in range(G)])
+    src = rng.uniform(0.05, 1.0, size=(G, n_reg))
+    flux0 = rng.uniform(0.5, 1.5, size=(G, n_reg))
+    bc = rng.uniform(0.0, 0.3, size=(n_plane, G, bcpg))
+    res = []
+    for pair in (True, False):
+        sw = _sweeper(flat, boundary_update=0, kernel=4)
+        sw.set_xs(0, xstr, xstr_src=xstr, xs_self=xself)
+        sw.set_source(0, src)
+        sw.set_flux(0, flux0)
+        for ip in range(n_plane):
+            sw.set_boundary(ip, 0, bc[ip])
+        if pair:
+            sw.sweep(0, 2, n_inner=n_inner, tally_mode=1)
+        else:
+            for g in range(2):
+                sw.sweep(g, 1, n_inner=n_inner, tally_mode=1)
+        out = [sw.get_flux(0, 2)]
+        for g in range(2):
+            out.append(np.stack([sw.get_boundary(ip, g, 1)[0] for ip in range(n_plane)]))
+            out.extend(sw.get_coarse(g))
+        res.append(out)
+        sw.close()
+    for x, y in zip(*res):
+        _close(x, y, atol=1e-13)

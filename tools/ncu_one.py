@@ -21,6 +21,9 @@ sw.set_xs(0, arr["xs_tr"], xstr_src=arr["xs_tr"], xs_self=arr["xs_self"])
 sw.set_source(0, bench.synthetic_source(arr, G, n_reg)); sw.set_flux(0, np.ones((G, n_reg)))
 for ip in range(sw.n_plane):
     sw.set_boundary(ip, 0, np.full((G, bcpg), 1.0 / (4 * np.pi)))
+if a.tally == 2:  # 2D3D correction factors need the homogenised Sn cross sections (any positive values do here)
+    ncell = int(arr["n_plane"][0]) * int(arr["n_cell_plane"][0])
+    sw.set_sn_xs(0, np.full((G, ncell), 0.5))
 for _ in range(a.reps):
     sw.sweep(a.group, 1, n_inner=a.n_inner, tally_mode=a.tally)
     sw.synchronize()
