@@ -19,6 +19,10 @@
  *                                + BoundaryCondition::update          core/source_isotropic.cpp:21-57,
  *                                                                     core/boundary_condition.cpp:145-191
  *   mocb200_get_coarse        <- moc::Current::post_ray tallies       sweepers/moc/moc_current_worker.hpp:202-264
+ *   mocb200_set_sweep_inputs,
+ *   mocb200_get_sweep_results <- everything MoCSweeper::sweep reads    sweepers/moc/moc_sweeper.cpp:197-219
+ *                                from / leaves in source_, flux_(:, g), boundary_[plane], coarse_data_
+ *                                (the single-array calls above, fused: one copy each way, one synchronisation)
  *   mocb200_set_sn_xs,
  *   mocb200_get_corrections   <- cmdo::CurrentCorrections                sweepers/cmdo/correction_worker.hpp:109-246,
  *                                                                     sweepers/cmdo/correction_worker.cpp:32-158
