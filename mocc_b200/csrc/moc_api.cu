@@ -870,7 +870,7 @@ ChunkFn pick_chunk_kernel(int np, int nw, int tally)
     return nullptr;
 }
 
-constexpr int kChunkSmemBudget = 232448 - 14336; // opt-in dynamic shared memory per CTA minus the static part
+constexpr int kChunkSmemBudget = 232448 - 12800; // opt-in dynamic shared memory per CTA minus the static part
 
 // launch geometry of the chunk kernel for a list: segments a team stages at once, warps per team,
 // teams per CTA
@@ -882,6 +882,9 @@ void chunk_geometry(int max_nseg, int np, int cap_opt, bool tally, int *caps, in
     c = std::min(c, cap_limit);
     if (cap_opt > 0)
         c = std::min(c, (cap_opt + 31) & ~31);
+    static const char *force_cap = getenv("MOCB200_CHUNK_CAP"); // tuning hook: staging cap in segments
+    if (force_cap && atoi(force_cap) > 0)
+        c = std::min(c, (atoi(force_cap) + 31) & ~31);
     *caps  = c;
     *nw    = c >= 256 ? 2 : 1;
     static const char *force_nw = getenv("MOCB200_CHUNK_NW"); // tuning hook: warps per track (1 or 2)

@@ -39,16 +39,16 @@
 namespace mocb200 {
 
 constexpr int kChunkMaxTeam  = 2;  // warps cooperating on one track (3 and 4 measured slower: profiles/r1/tuning.md)
-constexpr int kChunkMaxTeams = 14; // teams per CTA
+constexpr int kChunkMaxTeams = 16; // teams per CTA
 #ifndef MOCB200_CHUNK_ODD_L
 #define MOCB200_CHUNK_ODD_L 1
 #endif
 constexpr int kChunkOddL = MOCB200_CHUNK_ODD_L; // 1: odd chunk length (conflict-free shared-memory strides)
-// warps per CTA: the register budget per thread follows (1-2 warps per track: 448 threads, 146 registers;
+// warps per CTA: the register budget per thread follows (1-2 warps per track: 512 threads, 128 registers;
 // 3: 672 threads, 97 registers; 4: 896 threads, 73 registers)
 __host__ __device__ constexpr int chunk_max_warps(int nw)
 {
-    return nw <= 2 ? 14 : (nw == 3 ? 21 : 28);
+    return nw <= 2 ? 16 : (nw == 3 ? 21 : 28);
 }
 
 // One (track, polar bundle) of the chunk kernel: everything a warp needs to start the track in ONE
