@@ -141,30 +141,44 @@ __device__ __forceinline__ void chunk_compose(const double *exb, const double *q
     }
 }
 
-// inclusive scans over the 32 lanes of a warp: (Af, Bf) prefix (forward), (Ab, Bb) suffix (backward)
+// inclusive scans over the 32 lanes of a warp: (Af, Bf) prefix (forward), (Ab, Bb) suffix (backward).
+// Butterfly form: at step s a lane exchanges the TOTAL map of its 2s-aligned block of s lanes with lane ^ s
+// (three values: the product of A and the forward / backward constant term) and extends its prefix (upper
+// half) or suffix (lower half) by the partner block: 6 shuffles of 32 bits per value triple and step instead
+// of the 8 of a Kogge-Stone scan of two pairs -- shuffles are a third of the kernel's shared-memory wavefronts.
 template <int P>
 __device__ __forceinline__ void chunk_scan(int lane, const double (&A)[P], double (&Af)[P], double (&Bf)[P],
                                            double (&Ab)[P], double (&Bb)[P])
 {
+    double TA[P], TF[P], TB[P]; // total map of the lane's current block: x -> TA x + TF (forward), TA x + TB (backward)
 #pragma unroll
-    for (int p = 0; p < P; p++)
+    for (int p = 0; p < P; p++) {
         Af[p] = A[p], Ab[p] = A[p];
+        TA[p] = A[p], TF[p] = Bf[p], TB[p] = Bb[p];
+    }
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) {
+        const bool upper = (lane & s) != 0; // the partner block holds the LOWER segments
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            const double Ae = __shfl_up_sync(0xffffffffu, Af[p], s);
-            const double Be = __shfl_up_sync(0xffffffffu, Bf[p], s);
-            const double Ah = __shfl_down_sync(0xffffffffu, Ab[p], s);
-            const double Bh = __shfl_down_sync(0xffffffffu, Bb[p], s);
-            if (lane >= s) { // mine o earlier
-                Bf[p] = fma(Af[p], Be, Bf[p]);
-                Af[p] *= Ae;
+            const double oA = __shfl_xor_sync(0xffffffffu, TA[p], s);
+            const double oF = __shfl_xor_sync(0xffffffffu, TF[p], s);
+            const double oB = __shfl_xor_sync(0xffffffffu, TB[p], s);
+            if (upper) {
+                // forward: the lower block comes first, then my prefix
+                Bf[p] = fma(Af[p], oF, Bf[p]);
+                Af[p] *= oA;
+                // totals of the merged block: forward lower then upper (mine), backward upper (mine) then lower
+                TF[p] = fma(TA[p], oF, TF[p]);
+                TB[p] = fma(oA, TB[p], oB);
+            } else {
+                // backward: the upper block comes first, then my suffix
+                Bb[p] = fma(Ab[p], oB, Bb[p]);
+                Ab[p] *= oA;
+                TF[p] = fma(oA, TF[p], oF);
+                TB[p] = fma(TA[p], oB, TB[p]);
             }
-            if (lane + s < 32) { // mine o higher
-                Bb[p] = fma(Ab[p], Bh, Bb[p]);
-                Ab[p] *= Ah;
-            }
+            TA[p] *= oA;
         }
     }
 }
