@@ -141,19 +141,21 @@ __device__ __forceinline__ void chunk_compose(const double *exb, const double *q
     }
 }
 
-// inclusive scans over the 32 lanes of a warp: (Af, Bf) prefix (forward), (Ab, Bb) suffix (backward).
+// Scans over the 32 lanes of a warp. In: the map of the lane's own chunk, x -> A x + Bf (forward), A x + Bb
+// (backward). Out: the EXCLUSIVE prefix (Ef: the chunks of the lower lanes, forward) and suffix (Eb: the chunks
+// of the higher lanes, backward) and, in every lane, the total map of the warp (TA, TF, TB).
 // Butterfly form: at step s a lane exchanges the TOTAL map of its 2s-aligned block of s lanes with lane ^ s
-// (three values: the product of A and the forward / backward constant term) and extends its prefix (upper
-// half) or suffix (lower half) by the partner block: 6 shuffles of 32 bits per value triple and step instead
-// of the 8 of a Kogge-Stone scan of two pairs -- shuffles are a third of the kernel's shared-memory wavefronts.
+// (three values) and extends its prefix (upper half) or suffix (lower half) by the partner block: 6 shuffles
+// of 32 bits per polar angle and step instead of the 8 of a Kogge-Stone scan of two pairs, and no final shift
+// -- shuffles are a third of the kernel's shared-memory wavefronts.
 template <int P>
-__device__ __forceinline__ void chunk_scan(int lane, const double (&A)[P], double (&Af)[P], double (&Bf)[P],
-                                           double (&Ab)[P], double (&Bb)[P])
+__device__ __forceinline__ void chunk_scan(int lane, const double (&A)[P], const double (&Bf)[P], const double (&Bb)[P],
+                                           double (&EfA)[P], double (&EfB)[P], double (&EbA)[P], double (&EbB)[P],
+                                           double (&TA)[P], double (&TF)[P], double (&TB)[P])
 {
-    double TA[P], TF[P], TB[P]; // total map of the lane's current block: x -> TA x + TF (forward), TA x + TB (backward)
 #pragma unroll
     for (int p = 0; p < P; p++) {
-        Af[p] = A[p], Ab[p] = A[p];
+        EfA[p] = 1.0, EfB[p] = 0.0, EbA[p] = 1.0, EbB[p] = 0.0;
         TA[p] = A[p], TF[p] = Bf[p], TB[p] = Bb[p];
     }
 #pragma unroll
@@ -165,16 +167,16 @@ __device__ __forceinline__ void chunk_scan(int lane, const double (&A)[P], doubl
             const double oF = __shfl_xor_sync(0xffffffffu, TF[p], s);
             const double oB = __shfl_xor_sync(0xffffffffu, TB[p], s);
             if (upper) {
-                // forward: the lower block comes first, then my prefix
-                Bf[p] = fma(Af[p], oF, Bf[p]);
-                Af[p] *= oA;
+                // forward: the lower block comes first, then what I already have below me
+                EfB[p] = fma(EfA[p], oF, EfB[p]);
+                EfA[p] *= oA;
                 // totals of the merged block: forward lower then upper (mine), backward upper (mine) then lower
                 TF[p] = fma(TA[p], oF, TF[p]);
                 TB[p] = fma(oA, TB[p], oB);
             } else {
-                // backward: the upper block comes first, then my suffix
-                Bb[p] = fma(Ab[p], oB, Bb[p]);
-                Ab[p] *= oA;
+                // backward: the upper block comes first, then what I already have above me
+                EbB[p] = fma(EbA[p], oB, EbB[p]);
+                EbA[p] *= oA;
                 TF[p] = fma(oA, TF[p], oF);
                 TB[p] = fma(TA[p], oB, TB[p]);
             }
@@ -556,23 +558,20 @@ __global__ void __launch_bounds__(32 * chunk_max_warps(NW), 1) sweep_chunk_kerne
                      const double (&eb)[P], double (&out_fwd)[P], double (&out_bwd)[P]) {
         const int L  = ((n + T - 1) / T) | kChunkOddL;
         const int lo = min(tl * L, n), hi = min(lo + L, n);
-        double A[P], Af[P], Bf[P], Ab[P], Bb[P];
+        double A[P], Bf[P], Bb[P], EfA[P], EfB[P], EbA[P], EbB[P], TA[P], TF[P], TB[P];
         chunk_compose<P>(exb, qb, lo, hi, A, Bf, Bb);
-        chunk_scan<P>(lane, A, Af, Bf, Ab, Bb);
+        chunk_scan<P>(lane, A, Bf, Bb, EfA, EfB, EbA, EbB, TA, TF, TB);
         double cfw[P], ebw[P];
 #pragma unroll
         for (int p = 0; p < P; p++)
             cfw[p] = cf[p], ebw[p] = eb[p];
         if (NW > 1) { // maps of the other warps of the team: forward through the lower, backward through the higher ones
-            if (lane == 31) {
+            if (lane == 0) { // every lane holds the warp's total map
 #pragma unroll
-                for (int p = 0; p < P; p++)
-                    s_tot[team][wl][p][0] = Af[p], s_tot[team][wl][p][1] = Bf[p];
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int p = 0; p < P; p++)
-                    s_tot[team][wl][p][2] = Ab[p], s_tot[team][wl][p][3] = Bb[p];
+                for (int p = 0; p < P; p++) {
+                    s_tot[team][wl][p][0] = TA[p], s_tot[team][wl][p][1] = TF[p];
+                    s_tot[team][wl][p][2] = TA[p], s_tot[team][wl][p][3] = TB[p];
+                }
             }
             team_sync();
 #pragma unroll
@@ -595,13 +594,9 @@ __global__ void __launch_bounds__(32 * chunk_max_warps(NW), 1) sweep_chunk_kerne
         double psi_f[P], psi_b[P];
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            const double of = fma(Af[p], cfw[p], Bf[p]); // flux leaving this lane's chunk, forward
-            const double ob = fma(Ab[p], ebw[p], Bb[p]); // ... backward
-            const double in_f = __shfl_up_sync(0xffffffffu, of, 1);
-            const double in_b = __shfl_down_sync(0xffffffffu, ob, 1);
-            psi_f[p]   = lane == 0 ? cfw[p] : in_f;
-            psi_b[p]   = lane == 31 ? ebw[p] : in_b;
-            out_fwd[p] = of;
+            psi_f[p]   = fma(EfA[p], cfw[p], EfB[p]); // flux entering this lane's chunk, forward
+            psi_b[p]   = fma(EbA[p], ebw[p], EbB[p]); // ... backward
+            out_fwd[p] = fma(TA[p], cfw[p], TF[p]);   // flux leaving the warp's lanes, forward (every lane)
         }
         if (TALLY == 0) {
             chunk_walk<P>(exb, qb, ab, lo, hi, wt, psi_f, psi_b);
