@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +40,7 @@ struct TrackList { // one launch of the track kernel: units of one (unique plane
     ChunkUnit *d_cunits = nullptr; // self-contained descriptors of the same units (chunk kernel)
     int2 *d_pinfo       = nullptr; // per plane of the list: {macroplane, first FSR}
     int4 *d_len_begin   = nullptr; // per unit and polar angle: start of that angle's own segment lengths
+    std::vector<int32_t> nseg_desc; // track lengths, longest first (staging-cap choice of the chunk kernel)
     double *d_cache    = nullptr; // attenuation cache of this list (CACHED kernel)
 };
 
@@ -558,6 +560,8 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                     tl.unique = u, tl.phase = phase, tl.np = np;
                     tl.n_units  = (int32_t)units.size();
                     tl.max_nseg = units.front().nseg;
+                    for (const auto &tu : units)
+                        tl.nseg_desc.push_back(tu.nseg);
                     tl.n_planes = (int32_t)planes.size();
                     int64_t segs = 0;
                     for (const auto &tu : units)
@@ -874,12 +878,42 @@ constexpr int kChunkSmemBudget = 232448 - 12800; // opt-in dynamic shared memory
 
 // launch geometry of the chunk kernel for a list: segments a team stages at once, warps per team,
 // teams per CTA
-void chunk_geometry(int max_nseg, int np, int cap_opt, bool tally, int *caps, int *nw, int *teams)
+void chunk_geometry(const std::vector<int32_t> &nseg_desc, int np, int cap_opt, bool tally, int *caps, int *nw,
+                    int *teams)
 {
+    const int max_nseg  = nseg_desc.empty() ? 32 : nseg_desc.front();
     const int per_seg   = 8 * (np + 2) + 8 + (tally ? 4 : 0);
     const int cap_limit = ((kChunkSmemBudget / 4) / per_seg) & ~31; // at least 4 tracks in flight per SM
     int c = (max_nseg + 31) & ~31;
     c = std::min(c, cap_limit);
+    // Shared memory bounds the tracks in flight per SM. Staging the longest tracks whole is not always best: a
+    // smaller cap lets more teams run and only the few tracks above it pay a second pass (super-blocks).
+    // Model: time ~ (1 + share of the segments in tracks above the cap) / teams^0.75 (measured on C5G7-2D:
+    // cap 768 / 7 teams 0.1392 ms, 672 / 8 teams 0.1362, 640 / 8 0.143, 576 / 9 0.152).
+    if (c >= 256 && cap_opt == 0) {
+        const int max_teams = std::min(chunk_max_warps(2) / 2, kChunkMaxTeams);
+        double total = 0.0;
+        for (int32_t n : nseg_desc)
+            total += n;
+        auto teams_of = [&](int cap) { return std::min<int>(max_teams, kChunkSmemBudget / (int)chunk_warp_bytes(cap, np, tally)); };
+        double best = 1.0 / std::pow((double)std::max(1, teams_of(c)), 0.75);
+        int best_c  = c;
+        for (int k = teams_of(c) + 1; k <= max_teams; k++) {
+            const int cap = ((kChunkSmemBudget / k) / per_seg) & ~31; // largest cap that lets k teams run
+            if (cap < 256)
+                break;
+            double above = 0.0;
+            for (int32_t n : nseg_desc) {
+                if (n <= cap)
+                    break;
+                above += n;
+            }
+            const double t = (1.0 + above / std::max(total, 1.0)) / std::pow((double)k, 0.75);
+            if (t < best)
+                best = t, best_c = cap;
+        }
+        c = best_c;
+    }
     if (cap_opt > 0)
         c = std::min(c, (cap_opt + 31) & ~31);
     static const char *force_cap = getenv("MOCB200_CHUNK_CAP"); // tuning hook: staging cap in segments
@@ -1372,9 +1406,9 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1) {
                     int caps = 0, nw = 1, teams = 1;
                     const bool tl_tally = tally != MOCB200_TALLY_NONE;
-                    chunk_geometry(tl.max_nseg, tl.np, h->opt.chunk_cap, tl_tally, &caps, &nw, &teams);
+                    chunk_geometry(tl.nseg_desc, tl.np, h->opt.chunk_cap, tl_tally, &caps, &nw, &teams);
                     if (h->opt.chunk_cap < 0) // test hook: negative cap = that cap with two-warp teams
-                        chunk_geometry(tl.max_nseg, tl.np, -h->opt.chunk_cap, tl_tally, &caps, &nw, &teams), nw = 2,
+                        chunk_geometry(tl.nseg_desc, tl.np, -h->opt.chunk_cap, tl_tally, &caps, &nw, &teams), nw = 2,
                             teams = std::min(teams, chunk_max_warps(2) / 2);
                     const int cgrid =
                         (int)std::max<int64_t>(1, std::min<int64_t>((warps + teams - 1) / teams, h->track_grid));
