@@ -8,26 +8,31 @@
 // for one energy group per launch (the reference's sweep(group) contract) on the attenuation
 // cache (a = exp_table(-tau) evaluated once per cross-section upload, see exp_cache_kernel).
 //
-// What bounds a per-group sweep on B200 is neither HBM nor FP64 but the SM's load/store data
-// pipe: every segment needs one scattered 8-byte q-bar gather and one scattered FP64 reduction
+// What a per-group sweep costs on B200 is neither HBM nor FP64 but the SM's load/store data pipe and
+// latency: every segment needs one scattered 8-byte q-bar gather and one scattered FP64 reduction
 // (profiles/microbench/ubench2_b200.jsonl: 31 resp. 57 cycles per warp instruction that touches 32
-// distinct sectors). The warp-block kernel of moc_sweep_kernel.cuh adds to that two passes over
-// every 128-segment block, a 5-step shuffle scan per block and shared-memory transposes: ~275
-// warp instructions per 32 segments. Here a warp still owns one track, but
-//   * the track's attenuation stream (8 P bytes per segment, contiguous in the cache) is copied
-//     into shared memory by ONE TMA bulk copy (cp.async.bulk + mbarrier): it never touches the
-//     load/store pipe on the way in and is read from HBM exactly once per inner sweep;
-//   * q-bar is gathered with the lanes on 32 CONSECUTIVE segments (neighbouring segments lie in
-//     the same pin: few distinct sectors per instruction) and parked in shared memory;
-//   * lane i then owns the CONTIGUOUS chunk [i L, (i+1) L) of the track (L odd: conflict-free
-//     shared-memory strides), composes the affine maps of its chunk serially, ONE shuffle scan
-//     per track (prefix: forward, suffix: backward) yields the flux entering every chunk in both
-//     directions, and the lane walks its chunk forward and backward exactly like the reference
-//     loop, leaving the summed contribution of every segment in shared memory;
+// distinct sectors), shared-memory traffic for the lane-owned chunks, and the scan's shuffles. The
+// warp-block kernel of moc_sweep_kernel.cuh spends two passes over every 128-segment block, a 5-step
+// scan per block and shared-memory transposes: ~275 warp instructions per 32 segments. Here a TEAM
+// of NW warps (2 for long tracks) owns one track:
+//   * the track's attenuation block (8 P bytes per segment, contiguous in the cache) and its FSR ids are
+//     copied into shared memory by TMA bulk copies (cp.async.bulk + mbarrier): read from HBM exactly
+//     once per inner sweep, never through registers;
+//   * q-bar is gathered with the lanes on CONSECUTIVE segments (neighbouring segments lie in the same
+//     pin: few distinct sectors per instruction) by 8-byte cp.async straight into shared memory;
+//   * lane i owns the CONTIGUOUS chunk [i L, (i+1) L) of the track (L odd: conflict-free shared-memory
+//     strides), composes the affine maps of its chunk serially; ONE butterfly shuffle scan per warp
+//     (exclusive prefix: forward, suffix: backward; warp totals exchanged through shared memory) yields
+//     the flux entering every chunk in both directions; the lane walks its chunk forward and backward
+//     exactly like the reference loop, leaving the summed contribution of every segment in shared memory;
 //   * the tally is reduced into global memory again with the lanes on consecutive segments:
 //     ONE red.global.add.f64 per segment for both directions and all polar angles.
-// Tracks longer than the shared-memory capacity of a warp are cut into super-blocks chained by
-// a carried flux (a first pass over the super-blocks in reverse order chains the backward flux).
+// Work items are pulled from a global counter; the next item's descriptor, weights and incoming boundary
+// flux are prefetched by cp.async into a shared-memory mailbox, its FSR ids by TMA during the current
+// item's compute, its attenuations and q-bar behind the current item's reductions.
+// Tracks longer than the staging capacity of a team are cut into super-blocks chained by a carried flux
+// (a first pass over the super-blocks in reverse order chains the backward flux); the capacity is chosen
+// per launch list from the track-length distribution (moc_api.cu: chunk_geometry).
 #pragma once
 
 #include <cstdint>

@@ -1,5 +1,8 @@
 #include "cuda_moc_sweeper.hpp"
 
+#include <chrono>
+#include <cstdio>
+
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -137,6 +140,12 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
 
 CudaMoCSweeper::~CudaMoCSweeper()
 {
+    if (n_sweep_calls_ > 0) {
+        std::printf("CudaMoCSweeper: %ld sweep(group) calls; wall-clock inside them: upload %.3f s, enqueue %.3f s, "
+                    "host work between inners %.3f s, device wait + download + post-processing %.3f s; device sweep "
+                    "kernels %.3f s\n",
+                    n_sweep_calls_, t_upload_, t_enqueue_, t_host_mid_, t_download_, device_sweep_ms_ * 1e-3);
+    }
     for (auto &p : parts_)
         if (p.h)
             mocb200_destroy(p.h);
@@ -234,29 +243,46 @@ void CudaMoCSweeper::sweep(int group)
     timer_.tic();
     timer_sweep_.tic();
 
+    using clk = std::chrono::steady_clock;
+    auto since = [](clk::time_point t0) { return std::chrono::duration<double>(clk::now() - t0).count(); };
+    n_sweep_calls_++;
     flux_1g_.reference(flux_(blitz::Range::all(), group));
+    auto t0 = clk::now();
     upload_group(group);
+    t_upload_ += since(t0);
     const int tally = tally_mode();
     auto run = [&](int g0, int gc) {
         // every mocb200_sweep only enqueues work on its device's stream: the GPUs sweep concurrently
         if (split_last_inner() && tally != MOCB200_TALLY_NONE) {
             // the host refreshes data between the plain inners and the tallying one
+            auto t1 = clk::now();
             if (n_inner_ > 1) {
                 for (const Part &p : parts_)
                     check(p, mocb200_sweep(p.h, g0, gc, (int)n_inner_ - 1, MOCB200_TALLY_NONE, 0), "mocb200_sweep");
+                t_enqueue_ += since(t1);
+                t1 = clk::now();
                 for (int ig = g0; ig < g0 + gc; ig++)
                     download_flux(ig);
+                t_download_ += since(t1);
             }
+            t1 = clk::now();
             for (int ig = g0; ig < g0 + gc; ig++)
                 before_last_inner(ig);
+            t_host_mid_ += since(t1);
+            t1 = clk::now();
             for (const Part &p : parts_)
                 check(p, mocb200_sweep(p.h, g0, gc, 1, tally, 0), "mocb200_sweep");
+            t_enqueue_ += since(t1);
         } else {
+            auto t1 = clk::now();
             for (const Part &p : parts_)
                 check(p, mocb200_sweep(p.h, g0, gc, (int)n_inner_, tally, 0), "mocb200_sweep");
+            t_enqueue_ += since(t1);
         }
+        auto t2 = clk::now();
         for (int ig = g0; ig < g0 + gc; ig++)
             download_group(ig, tally);
+        t_download_ += since(t2);
         double ms_max = 0.0;
         for (const Part &p : parts_) {
             double ms = 0.0;

@@ -92,6 +92,10 @@ protected:
     std::vector<int> plane_xs_offset_; // CurrentCorrections::mplane_offset_
     std::vector<double> col_, cur_, sflux_;
     double device_sweep_ms_ = 0.0;
+    // wall-clock split of sweep(): host->device, host work between the inners (2D3D), waiting for the
+    // device + device->host, host post-processing; reported at destruction
+    double t_upload_ = 0.0, t_host_mid_ = 0.0, t_download_ = 0.0, t_enqueue_ = 0.0;
+    long n_sweep_calls_ = 0;
     mocb200_stats stats_{};
 };
 
