@@ -272,7 +272,6 @@ def main():
         step_device()
         e1.record(stream)
     barrier()
-    clocks = sampler.stop() if sampler else None
     ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     launches = sw.stats()["kernel_launches"] - launches0
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -319,6 +318,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = updates_step * args.steps / float(t.item())
+    # the clock sampler covers the device-resident AND the end-to-end timed regions (both under load)
+    clocks = sampler.stop() if sampler else None
 
     # ---- reference CPU sweep on this box's host cores (rank 0, N = 1): one step of the same workload ----
     cpu = None
