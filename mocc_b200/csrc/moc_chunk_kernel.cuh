@@ -279,6 +279,8 @@ struct ChunkTallyCtx {
     int seg_begin, nseg, k_off; // track position of the staged block
     int plane, first_reg, grel, g;
     int ang[4];
+    double cw[4][2], fw[4][2]; // current / surface-flux weights of the bundle's angles (X, Y normal)
+    int surf_off;
 };
 
 // The walk of the last inner: as chunk_walk, plus moc::Current::post_ray (moc_current_worker.hpp:202-264)
@@ -292,16 +294,9 @@ __device__ __forceinline__ void chunk_walk_tally(const double *exb, const double
     const ChunkArgs &a = *c.a;
     if (lo >= hi)
         return;
-    const int GP    = a.GP;
-    const int nslot = 2 * a.n_ang;
-    double cw[P][2], fw[P][2];
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-        const size_t o = ((size_t)c.plane * a.n_ang + c.ang[p]) * 2;
-        cw[p][0] = a.cur_w[o], cw[p][1] = a.cur_w[o + 1];
-        fw[p][0] = a.flx_w[o], fw[p][1] = a.flx_w[o + 1];
-    }
-    const int surf_off = a.plane_surf_offset[c.plane];
+    const int GP       = a.GP;
+    const int nslot    = 2 * a.n_ang;
+    const int surf_off = c.surf_off;
     auto tally_cross = [&](const Cross &x, const double (&psi)[P], int dir) {
         const int norm = x.surf & 1;
         const int surf = x.surf >> 1;
@@ -309,8 +304,8 @@ __device__ __forceinline__ void chunk_walk_tally(const double *exb, const double
         double cs = 0.0, fsum = 0.0;
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            cs   = fma(psi[p], norm ? cw[p][1] : cw[p][0], cs);
-            fsum = fma(psi[p], norm ? fw[p][1] : fw[p][0], fsum);
+            cs   = fma(psi[p], norm ? c.cw[p][1] : c.cw[p][0], cs);
+            fsum = fma(psi[p], norm ? c.fw[p][1] : c.fw[p][0], fsum);
         }
         // forward adds, backward subtracts (moc_current_worker.hpp:230-231); the corrections worker also
         // subtracts the backward SURFACE FLUX (correction_worker.hpp:136-137, 194-195)
@@ -349,55 +344,54 @@ __device__ __forceinline__ void chunk_walk_tally(const double *exb, const double
     Cross xf = xfl[ci_f], xb = xbl[ci_b];
     auto next_f = [&]() { xf = xfl[++ci_f]; };
     auto next_b = [&]() { xb = xbl[++ci_b]; };
-    // ---- forward ----
-    for (int k = lo; k < hi; k++) {
-        const int kt = c.k_off + k; // forward flux at the node in front of segment kt
-        while (xf.node == kt) {
+    // ---- both directions interleaved, as in chunk_walk: forward at kf, backward at kb ----
+    const int len = hi - lo;
+    for (int j = 0; j < len; j++) {
+        const int kf = lo + j, kb = hi - 1 - j;
+        const int ktf = c.k_off + kf;            // forward flux at the node in front of segment ktf
+        const int ktb = c.k_off + kb;
+        const int nb  = nseg - 1 - ktb;          // segments walked by the backward sweep so far
+        while (xf.node == ktf) {
             tally_cross(xf, psi_f, 0);
             next_f();
         }
-        double e[P];
-        load_ex<P>(exb, k, e);
-        const double q = qb[k];
-        double sf = 0.0;
+        while (xb.node == nb) {
+            tally_cross(xb, psi_b, 1);
+            next_b();
+        }
+        double ef[P], er[P];
+        load_ex<P>(exb, kf, ef);
+        load_ex<P>(exb, kb, er);
+        const double qf = qb[kf], qr = qb[kb];
+        double sf = 0.0, sr = 0.0;
+        if (kf > kb) // second visits: add to what the other direction left
+            sf = ab[kf], sr = ab[kb];
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            const double d = (psi_f[p] - q) * (1.0 - e[p]);
-            psi_f[p] -= d;
-            sf = fma(d, wt[p], sf);
-            if (TALLY == 2)
-                dsum_add(c.fb[k] + c.first_reg, p, 0, d);
+            const double df = (psi_f[p] - qf) * (1.0 - ef[p]);
+            const double dr = (psi_b[p] - qr) * (1.0 - er[p]);
+            psi_f[p] -= df;
+            psi_b[p] -= dr;
+            sf = fma(df, wt[p], sf);
+            sr = fma(dr, wt[p], sr);
+            if (TALLY == 2) {
+                dsum_add(c.fb[kf] + c.first_reg, p, 0, df);
+                dsum_add(c.fb[kb] + c.first_reg, p, 1, dr);
+            }
         }
-        ab[k] = sf;
-        if (kt == nseg - 1) { // far end of the ray
+        if (kf == kb) {
+            ab[kf] = sf + sr;
+        } else {
+            ab[kf] = sf;
+            ab[kb] = sr;
+        }
+        if (ktf == nseg - 1) { // far end of the ray
             while (xf.node == nseg) {
                 tally_cross(xf, psi_f, 0);
                 next_f();
             }
         }
-    }
-    // ---- backward ----
-    for (int k = hi - 1; k >= lo; k--) {
-        const int kt = c.k_off + k;
-        const int nb = nseg - 1 - kt; // segments walked by the backward sweep so far
-        while (xb.node == nb) {
-            tally_cross(xb, psi_b, 1);
-            next_b();
-        }
-        double e[P];
-        load_ex<P>(exb, k, e);
-        const double q = qb[k];
-        double sr = ab[k];
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-            const double d = (psi_b[p] - q) * (1.0 - e[p]);
-            psi_b[p] -= d;
-            sr = fma(d, wt[p], sr);
-            if (TALLY == 2)
-                dsum_add(c.fb[k] + c.first_reg, p, 1, d);
-        }
-        ab[k] = sr;
-        if (kt == 0) { // near end of the ray
+        if (ktb == 0) { // near end of the ray
             while (xb.node == nseg) {
                 tally_cross(xb, psi_b, 1);
                 next_b();
@@ -563,6 +557,24 @@ __global__ void __launch_bounds__(32 * chunk_max_warps(NW), 1) sweep_chunk_kerne
                      const double (&eb)[P], double (&out_fwd)[P], double (&out_bwd)[P]) {
         const int L  = ((n + T - 1) / T) | kChunkOddL;
         const int lo = min(tl * L, n), hi = min(lo + L, n);
+        ChunkTallyCtx c;
+        if (TALLY != 0) { // requested first: the weights' global latency hides behind compose and scan
+            c.a = &a, c.fb = fbuf + fi * caps;
+            c.n_fw = k->u.n_fw, c.n_bw = k->u.n_bw;
+            c.xl = (c.n_fw + c.n_bw + 2 <= caps / 2) ? xsm : a.cross + k->u.cross_begin;
+            c.seg_begin = k->u.seg_begin, c.nseg = k->u.nseg, c.k_off = k_off;
+            c.plane = k->pinfo.x, c.first_reg = k->pinfo.y, c.grel = k->grel, c.g = a.g_begin + k->grel;
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                c.ang[p] = k->u.ang[p];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const size_t o = ((size_t)c.plane * a.n_ang + c.ang[p]) * 2;
+                c.cw[p][0] = a.cur_w[o], c.cw[p][1] = a.cur_w[o + 1];
+                c.fw[p][0] = a.flx_w[o], c.fw[p][1] = a.flx_w[o + 1];
+            }
+            c.surf_off = a.plane_surf_offset[c.plane];
+        }
         double A[P], Bf[P], Bb[P], EfA[P], EfB[P], EbA[P], EbB[P], TA[P], TF[P], TB[P];
         chunk_compose<P>(exb, qb, lo, hi, A, Bf, Bb);
         chunk_scan<P>(lane, A, Bf, Bb, EfA, EfB, EbA, EbB, TA, TF, TB);
@@ -606,15 +618,6 @@ __global__ void __launch_bounds__(32 * chunk_max_warps(NW), 1) sweep_chunk_kerne
         if (TALLY == 0) {
             chunk_walk<P>(exb, qb, ab, lo, hi, wt, psi_f, psi_b);
         } else {
-            ChunkTallyCtx c;
-            c.a = &a, c.fb = fbuf + fi * caps;
-            c.n_fw = k->u.n_fw, c.n_bw = k->u.n_bw;
-            c.xl = (c.n_fw + c.n_bw + 2 <= caps / 2) ? xsm : a.cross + k->u.cross_begin;
-            c.seg_begin = k->u.seg_begin, c.nseg = k->u.nseg, c.k_off = k_off;
-            c.plane = k->pinfo.x, c.first_reg = k->pinfo.y, c.grel = k->grel, c.g = a.g_begin + k->grel;
-#pragma unroll
-            for (int p = 0; p < 4; p++)
-                c.ang[p] = k->u.ang[p];
             chunk_walk_tally<P, TALLY>(exb, qb, ab, lo, hi, wt, psi_f, psi_b, c);
         }
 #pragma unroll
