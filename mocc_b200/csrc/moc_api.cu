@@ -896,19 +896,22 @@ void chunk_geometry(const std::vector<int32_t> &nseg_desc, int np, int cap_opt, 
         for (int32_t n : nseg_desc)
             total += n;
         auto teams_of = [&](int cap) { return std::min<int>(max_teams, kChunkSmemBudget / (int)chunk_warp_bytes(cap, np, tally)); };
-        double best = 1.0 / std::pow((double)std::max(1, teams_of(c)), 0.75);
-        int best_c  = c;
-        for (int k = teams_of(c) + 1; k <= max_teams; k++) {
-            const int cap = ((kChunkSmemBudget / k) / per_seg) & ~31; // largest cap that lets k teams run
-            if (cap < 256)
-                break;
+        auto model = [&](int cap, int k) {
             double above = 0.0;
             for (int32_t n : nseg_desc) {
                 if (n <= cap)
                     break;
                 above += n;
             }
-            const double t = (1.0 + above / std::max(total, 1.0)) / std::pow((double)k, 0.75);
+            return (1.0 + above / std::max(total, 1.0)) / std::pow((double)std::max(1, k), 0.75);
+        };
+        double best = model(c, teams_of(c));
+        int best_c  = c;
+        for (int k = teams_of(c) + 1; k <= max_teams; k++) {
+            const int cap = ((kChunkSmemBudget / k) / per_seg) & ~31; // largest cap that lets k teams run
+            if (cap < 256)
+                break;
+            const double t = model(cap, k);
             if (t < best)
                 best = t, best_c = cap;
         }
