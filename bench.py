@@ -59,6 +59,10 @@ WORKLOADS = {
     "dense_a": ("C5G7 2-D dense-A (examples/c5g7_2d.xml with cg 16x4, spacing 0.02): 7 groups, n_inner 10, "
                 "coarse-current tally on the last inner",
                 ["solver/ang_quad@n_azimuthal=16", "solver/ang_quad@n_polar=4", "solver/sweeper/rays@spacing=0.02"]),
+    # BASELINE.json configs[4] at plane level: 9x9 checkerboard of the C5G7 assemblies with a reflector ring
+    # (tools/make_quarter_core.py); with --gpus N one such plane per GPU
+    "quarter_core": ("synthetic quarter core, 9x9 assemblies of 17x17 pins (C5G7 lattices, cg 8x2, spacing 0.05): "
+                     "7 groups, n_inner 10, coarse-current tally on the last inner", None),
 }
 
 
@@ -73,8 +77,17 @@ def workload_files(name="c5g7_2d"):
             raise RuntimeError("mocc_b200/bin/mocc_flatten missing: run __graft_entry__.build() where the "
                                "reference sources are available")
         tmp = flat + f".tmp{os.getpid()}"
-        sets = [x for s in WORKLOADS[name][1] for x in ("--set", s)]
-        subprocess.check_call([tool, "c5g7_2d.xml", tmp, "--xs"] + sets, cwd=inputs, stdout=subprocess.DEVNULL)
+        if WORKLOADS[name][1] is None:  # an authored input: generated next to the example's data files
+            work = os.path.join(CACHE, name)
+            os.makedirs(work, exist_ok=True)
+            subprocess.check_call(["cp", os.path.join(inputs, "c5g7.xsl"), work])
+            subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_quarter_core.py"),
+                                   os.path.join(inputs, "c5g7_2d.xml"), os.path.join(work, "in.xml")],
+                                  stdout=subprocess.DEVNULL)
+            subprocess.check_call([tool, "in.xml", tmp, "--xs"], cwd=work, stdout=subprocess.DEVNULL)
+        else:
+            sets = [x for s in WORKLOADS[name][1] for x in ("--set", s)]
+            subprocess.check_call([tool, "c5g7_2d.xml", tmp, "--xs"] + sets, cwd=inputs, stdout=subprocess.DEVNULL)
         os.replace(tmp, flat)
     return flat
 
