@@ -99,6 +99,9 @@ protected:
     mocb200_stats stats_{};
 };
 
+// XSMeshHomogenized::update() with the pin loop spread over the host threads (xs_update_parallel.cpp)
+void parallel_update(mocc::XSMeshHomogenized &xs);
+
 // The per-plane MoC sweeper of the 2D3D method on the B200: same interface as
 // cmdo::MoCSweeper_2D3D (src/sweepers/cmdo/moc_sweeper_2d3d.hpp:25-88), so that the reference's
 // PlaneSweeper_2D3D can hold it in place of the CPU class (plane_sweeper_2d3d_cuda.cpp).
