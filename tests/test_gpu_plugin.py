@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 SOLVE = os.path.join(ROOT, "mocc_b200", "bin", "mocc_b200_solve")
 
 
-def _solve(tmp_path, xml, sets):
+def _solve(tmp_path, xml, sets, extra_env=None):
     from mocc_b200 import load_arrays
     assert os.path.exists(SOLVE), "mocc_b200/bin/mocc_b200_solve missing: run __graft_entry__.build() with the reference"
     for d in (os.path.join(GOLDEN, "inputs"), os.path.join(ROOT, "mocc_b200", "bin", "inputs")):
@@ -32,7 +32,7 @@ def _solve(tmp_path, xml, sets):
     # One host thread, like the goldens: the reference's own 2D3D host path (OpenMP Sn sweep) converges along a
     # different k history with 1 thread than with >= 2 (k after 3 outers 0.988058 vs 0.984680 on mini2d3d, CPU
     # reference alone), so a thread-count mismatch would be mistaken for a sweeper difference.
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env = dict(os.environ, OMP_NUM_THREADS="1", **(extra_env or {}))
     r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return load_arrays(str(out))
@@ -71,6 +71,14 @@ def test_group_batched_solve_converges_to_reference(tmp_path):
 def test_2d3d_solve_matches_reference(tmp_path):
     """The reference's PlaneSweeper_2D3D around the CUDA MoC sweeper: k history of 12 outers and the MoC flux."""
     res = _solve(tmp_path, "mini2d3d.xml", ["solver/sweeper@type=2d3d_cuda"])
+    _check(res, _golden("mini2d3d_solve_ref.arrays.gz"), k_tol=1e-8, flux_tol=1e-7)
+
+
+def test_2d3d_rehomogenisation_is_bit_identical_to_the_reference_routine(tmp_path):
+    """The plugin's restatement of XSMeshHomogenized::update (mocc_b200/host/xs_update_parallel.cpp) next to the
+    reference's own per-pin routine, every update of a whole 2D3D solve: the plugin throws on the first differing
+    bit, and the solve still equals the golden."""
+    res = _solve(tmp_path, "mini2d3d.xml", ["solver/sweeper@type=2d3d_cuda"], extra_env={"MOCB200_CHECK_XS_UPDATE": "1"})
     _check(res, _golden("mini2d3d_solve_ref.arrays.gz"), k_tol=1e-8, flux_tol=1e-7)
 
 
