@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c5g7_2d", choices=sorted(WORKLOADS))
     ap.add_argument("--max-polar", type=int, default=0, help="polar angles bundled per track (0 = library default, 2)")
+    ap.add_argument("--cache-groups", type=int, default=0,
+                    help="groups the attenuation cache holds at once (0 = all that fit; 1 = what a problem too large for "
+                         "the device gets: rebuilt per sweep call)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -225,7 +228,8 @@ def main():
     gs = args.boundary == "gs"
     src = synthetic_source(arr, G, n_reg)
 
-    sw = Sweeper(arr, device=local, boundary_update=0 if gs else 1, kernel=args.kernel, max_polar=args.max_polar)
+    sw = Sweeper(arr, device=local, boundary_update=0 if gs else 1, kernel=args.kernel, max_polar=args.max_polar,
+                 cache_groups=args.cache_groups)
     # a dedicated non-default stream: the C ABI treats a NULL stream as "use the handle's own", and
     # torch events only see work on the stream they are recorded on
     stream = torch.cuda.Stream()
@@ -368,7 +372,8 @@ def main():
                        "mode": args.mode, "boundary_update": args.boundary, "segments": S, "resident_segments": n_useg,
                        "n_reg": n_reg, "groups": G, "n_inner": n_inner, "updates_per_step": updates_step,
                        "l2": "256 MB flush write between timed steps; device-resident inputs 450 MB > 126 MB L2",
-                       "kernel": kname, "bundled_segments": int(st["swept_segments"]), "max_polar": args.max_polar or 2},
+                       "kernel": kname, "bundled_segments": int(st["swept_segments"]), "max_polar": args.max_polar or 2,
+                       "cache_groups": args.cache_groups or G},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(ln.item()),
             "clocks": clocks,

@@ -165,7 +165,9 @@ typedef struct mocb200_options {
     int32_t kernel;          /* MOCB200_KERNEL_* */
     int32_t chunk_cap;       /* CHUNK kernel test hook: cap on the segments staged at once (0 = what fits), forces the
                                 super-block chaining of long tracks; negative = that cap with two-warp teams */
-    int32_t reserved[7];
+    int32_t cache_groups;    /* energy groups the attenuation cache holds at once: 0 = all if they fit in device memory,
+                                else as many as fit (>= 1; rebuilt per sweep call, 2 small launches per group); test hook */
+    int32_t reserved[6];
 } mocb200_options;
 
 /* Build the device-resident problem. The host arrays may be freed afterwards. */

@@ -97,6 +97,8 @@ struct mocb200_sweeper {
     int kernel = 0;       // MOCB200_KERNEL_* actually used
     int cache_layout = 0; // 0 = no cache allocated, 1 = group-major (GL 1), 8 = group-fastest (GL 8)
     std::vector<bool> cache_valid; // per group
+    int cache_slots = 0;           // groups the group-major cache holds at once (G when everything fits)
+    int cache_g0 = 0, cache_gn = 0; // groups resident when cache_slots < G: [cache_g0, cache_g0 + cache_gn)
     double *d_qg = nullptr, *d_tg = nullptr; // group-major q-bar / tally [G][n_reg]
     // 2D3D correction factors
     bool have_corr = false;
@@ -288,10 +290,17 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
         }
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
-        const bool fits = (double)bytes < 0.7 * (double)free_b;
+        // all groups if they fit, else as many as fit (the cache is then rebuilt for the groups of every sweep call)
+        int slots = h->G;
+        while (slots > 1 && (double)bytes * slots / h->G >= 0.7 * (double)free_b)
+            slots--;
+        if (opt.cache_groups > 0)
+            slots = std::min<int>(slots, opt.cache_groups);
+        const bool fits = (double)bytes * slots / h->G < 0.7 * (double)free_b;
+        h->cache_slots  = slots;
         if (!fits && h->kernel != MOCB200_KERNEL_AUTO)
-            return fail(h, MOCB200_ERR_INVALID, "attenuation cache (%lld MiB) does not fit in device memory",
-                        (long long)(bytes >> 20));
+            return fail(h, MOCB200_ERR_INVALID, "attenuation cache (%lld MiB per group) does not fit in device memory",
+                        (long long)((bytes / h->G) >> 20));
         h->kernel = !fits ? MOCB200_KERNEL_TRACK
                           : (h->kernel == MOCB200_KERNEL_CACHED ? MOCB200_KERNEL_CACHED : MOCB200_KERNEL_CHUNK);
     }
@@ -1242,6 +1251,12 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
     const bool cached     = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK;
     const bool group_major = cached && gl == 1;
 
+    if (cached && gl != 1 && h->cache_slots < h->G)
+        return fail(h, MOCB200_ERR_STATE, "group-batched sweeps need the attenuation cache of all groups (%d of %d fit)",
+                    h->cache_slots, h->G);
+    if (cached && g_count > h->cache_slots)
+        return fail(h, MOCB200_ERR_STATE, "%d groups per call but the attenuation cache holds %d", g_count, h->cache_slots);
+    const bool sliding = cached && h->cache_slots < h->G; // the cache holds the groups of this call only
     if (cached) {
         // (re)build the attenuation cache for groups whose cross sections changed
         if (h->cache_layout != gl) {
@@ -1249,16 +1264,20 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 if (tl.d_cache) {
                     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
                     CUDA_TRY(h, cudaFree(tl.d_cache));
-                    h->device_bytes -= tl.pseg * tl.np * tl.n_planes * (int64_t)(h->cache_layout == 1 ? h->G : h->GP) * 8;
+                    h->device_bytes -= tl.pseg * tl.np * tl.n_planes * (int64_t)(h->cache_layout == 1 ? h->cache_slots : h->GP) * 8;
                     tl.d_cache = nullptr;
                 }
-                const size_t bytes = (size_t)tl.pseg * tl.np * tl.n_planes * (gl == 1 ? h->G : h->GP) * 8;
+                const size_t bytes = (size_t)tl.pseg * tl.np * tl.n_planes * (gl == 1 ? h->cache_slots : h->GP) * 8;
                 CUDA_TRY(h, cudaMalloc((void **)&tl.d_cache, bytes));
                 h->device_bytes += (int64_t)bytes;
             }
             h->cache_layout = gl;
             h->cache_valid.assign(h->G, false);
             h->stats.device_bytes = h->device_bytes;
+        }
+        if (sliding && (h->cache_g0 != g_begin || h->cache_gn != g_count)) {
+            h->cache_valid.assign(h->G, false); // other groups are resident: this call's replace them
+            h->cache_g0 = g_begin, h->cache_gn = g_count;
         }
         bool dirty = false;
         for (int g = g_begin; g < g_begin + g_count; g++)
@@ -1270,7 +1289,8 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 c.planes = tl.d_planes, c.n_planes = tl.n_planes;
                 c.seg_len = h->d_pseg_len, c.seg_fsr = h->d_pseg_fsr, c.ang_rsintheta = h->d_rsin;
                 c.plane_first_reg = h->d_plane_first_reg, c.xstr = h->d_xstr;
-                c.g_begin = g_begin, c.g_count = g_count, c.cache_groups = h->G;
+                c.g_begin = g_begin, c.g_count = g_count, c.cache_groups = h->cache_slots;
+                c.cache_g0 = sliding ? g_begin : 0;
                 c.GP = h->GP, c.np = tl.np, c.group_major = gl == 1 ? 1 : 0;
                 c.cache = tl.d_cache, c.list_pseg = tl.pseg;
                 c.exp_table = h->d_exp, c.exp_n = h->exp_n, c.exp_min = h->exp_min, c.exp_max = h->exp_max;
@@ -1404,7 +1424,8 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 a.current = h->d_current, a.surface_flux = h->d_surfflux;
                 a.dsum = h->d_dsum, a.ssum = h->d_ssum;
                 a.scratch = h->d_scratch, a.scratch_per_warp = h->scratch_per_warp;
-                a.cache = tl.d_cache, a.list_pseg = tl.pseg, a.cache_groups = h->G;
+                a.cache = tl.d_cache, a.list_pseg = tl.pseg, a.cache_groups = h->cache_slots;
+                a.cache_g0 = sliding ? g_begin : 0;
                 a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
                 if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1) {
                     int caps = 0, nw = 1, teams = 1;
@@ -1422,7 +1443,8 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                     c.g_begin = g_begin, c.g_count = g_count, c.GP = h->GP, c.n_reg = h->n_reg;
                     c.q = h->d_qg, c.tally = h->d_tg, c.bc_in = bc_in, c.bc_out = bc_out;
                     c.scratch = h->d_scratch, c.scratch_per_warp = h->scratch_per_warp;
-                    c.cache = tl.d_cache, c.list_pseg = tl.pseg, c.cache_groups = h->G, c.caps = caps;
+                    c.cache = tl.d_cache, c.list_pseg = tl.pseg, c.cache_groups = h->cache_slots, c.caps = caps;
+                    c.cache_g0 = sliding ? g_begin : 0;
                     static const char *ex_mode = getenv("MOCB200_CHUNK_EX"); // tuning hook
                     c.ex_mode = ex_mode && ex_mode[0] == '1' ? 1 : 0;
                     c.xptr = h->d_xptr, c.cross = h->d_xcross, c.cur_w = h->d_curw, c.flx_w = h->d_flxw;

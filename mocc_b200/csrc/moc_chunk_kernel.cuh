@@ -256,7 +256,7 @@ struct ChunkArgs {
     int32_t scratch_per_warp;
     const double *cache; // attenuation cache of this list [plane][g][pos][P]
     int64_t list_pseg;
-    int32_t cache_groups;
+    int32_t cache_groups, cache_g0; // groups per plane in the cache, first group it holds
     int32_t caps; // segments a team stages at once
     int32_t ex_mode; // 0: attenuations by TMA bulk copy, 1: by 16-byte cp.async of all lanes (tuning)
     // coarse-mesh tallies of the last inner (TALLY 1: moc::Current, 2: cmdo::CurrentCorrections)
@@ -501,14 +501,14 @@ __global__ void __launch_bounds__(32 * chunk_max_warps(NW), 1) sweep_chunk_kerne
     auto issue_ex = [&](const ChunkWork *k, int k_off, int n) {
         if (a.ex_mode == 1) {
             const int g        = a.g_begin + k->grel;
-            const double *ex_g = a.cache + (((size_t)k->ipl * a.cache_groups + g) * a.list_pseg + k->u.cpos + k_off) * P;
+            const double *ex_g = a.cache + (((size_t)k->ipl * a.cache_groups + (g - a.cache_g0)) * a.list_pseg + k->u.cpos + k_off) * P;
             const int n16      = ((n + 3) & ~3) * P / 2;
 #pragma unroll 4
             for (int i = tl; i < n16; i += T)
                 cp_async_16(exb + 2 * i, ex_g + 2 * i);
         } else if (loader) {
             const int g        = a.g_begin + k->grel;
-            const double *ex_g = a.cache + (((size_t)k->ipl * a.cache_groups + g) * a.list_pseg + k->u.cpos) * P;
+            const double *ex_g = a.cache + (((size_t)k->ipl * a.cache_groups + (g - a.cache_g0)) * a.list_pseg + k->u.cpos) * P;
             const uint32_t bytes = (uint32_t)((n + 3) & ~3) * (uint32_t)P * 8u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar + 2, bytes);

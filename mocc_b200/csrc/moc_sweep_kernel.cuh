@@ -105,7 +105,7 @@ struct WarpArgs {
     // attenuation cache of this list: GL = 1 [plane][g][pos][P]; GL = 8 [plane][pos][P][GP]
     const double *cache;
     int64_t list_pseg;
-    int32_t cache_groups;
+    int32_t cache_groups, cache_g0; // groups per plane in the cache, first group it holds
     // exponential table (!CACHED)
     const double *exp_table;
     int32_t exp_n;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kWarpBlock, 1) sweep_warp_kernel(const WarpArg
             if (GL == 1) {
                 qv   = a.q + (size_t)grel * a.n_reg;
                 tv   = a.tally + (size_t)grel * a.n_reg;
-                ex_b = a.cache + (((size_t)ipl * a.cache_groups + g) * a.list_pseg + cpos) * P;
+                ex_b = a.cache + (((size_t)ipl * a.cache_groups + (g - a.cache_g0)) * a.list_pseg + cpos) * P;
             } else {
                 qv      = a.q + g;
                 tv      = a.tally + g;
@@ -666,7 +666,7 @@ struct CacheArgs {
     const double *ang_rsintheta;
     const int32_t *plane_first_reg;
     const double *xstr; // [n_reg][GP]
-    int32_t g_begin, g_count, cache_groups, GP, np, group_major;
+    int32_t g_begin, g_count, cache_groups, cache_g0, GP, np, group_major;
     double *cache;
     int64_t list_pseg;
     const double *exp_table;
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(512, 1) exp_cache_kernel(const CacheArgs a)
                     const double ex  = valid ? exp_interp(s_tab, t * nrs, c0, rspace) : 1.0;
                     size_t o;
                     if (a.group_major)
-                        o = (((size_t)ipl * a.cache_groups + g) * a.list_pseg + u.cpos + k) * P + p;
+                        o = (((size_t)ipl * a.cache_groups + (g - a.cache_g0)) * a.list_pseg + u.cpos + k) * P + p;
                     else
                         o = (((size_t)ipl * a.list_pseg + u.cpos + k) * P + p) * a.GP + g;
                     a.cache[o] = ex;

@@ -41,6 +41,7 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
             devices.push_back(cu.attribute("device").as_int(0));
     }
     opt.max_polar           = cu.attribute("max_polar").as_int(0);
+    opt.cache_groups        = cu.attribute("cache_groups").as_int(0);
     group_batch_            = cu.attribute("group_batch").as_bool(false);
     std::string kernel      = cu.attribute("kernel").as_string("auto");
     if (kernel == "auto")

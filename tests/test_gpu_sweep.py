@@ -397,3 +397,43 @@ def test_two_groups_per_call_on_the_chunk_kernel(case, n_inner):
         sw.close()
     for x, y in zip(*res):
         _close(x, y, atol=1e-13)
+
+
+@pytest.mark.parametrize("case", ["mini2d_gs", "mini3d_gs"])
+@pytest.mark.parametrize("slots", [1, 2])
+def test_sliding_attenuation_cache_equals_full_cache(case, slots):
+    """cache_groups < G (what a problem too large for the device gets): the cache is rebuilt for the groups of every
+    call; results equal those with all groups resident. Group-batched sweeps are refused."""
+    flat, gold = load_case(case)
+    G, n_reg, n_plane = (int(flat[k][0]) for k in ("n_group", "n_reg", "n_plane"))
+    bcpg = int(flat["bc_per_group"][0])
+    rng = np.random.default_rng(17)
+    xstr = np.stack([gold[f"xs_tr_{g}"] for g in range(G)])
+    xself = np.stack([gold[f"xs_self_{g}"] for g in range(G)])
+    src = rng.uniform(0.05, 1.0, size=(G, n_reg))
+    bc = rng.uniform(0.0, 0.3, size=(n_plane, G, bcpg))
+    res = []
+    for cg in (0, slots):
+        sw = _sweeper(flat, boundary_update=0, cache_groups=cg)
+        sw.set_xs(0, xstr, xstr_src=xstr, xs_self=xself)
+        sw.set_source(0, src)
+        sw.set_flux(0, np.ones((G, n_reg)))
+        for ip in range(n_plane):
+            sw.set_boundary(ip, 0, bc[ip])
+        for _ in range(2):  # two outers: every group's slot is evicted and rebuilt
+            for g in range(G):
+                sw.sweep(g, 1, n_inner=2, tally_mode=1)
+        if slots >= 2:
+            sw.sweep(0, 2, n_inner=1, tally_mode=0)  # two groups per call fit two slots
+        elif cg:
+            with pytest.raises(RuntimeError, match="attenuation cache holds"):
+                sw.sweep(0, 2, n_inner=1, tally_mode=0)
+        if cg:
+            with pytest.raises(RuntimeError, match="group-batched"):
+                sw.sweep(0, G, n_inner=1, tally_mode=0)
+        out = [sw.get_flux(0, G)]
+        out += [np.stack([sw.get_boundary(ip, g, 1)[0] for ip in range(n_plane)]) for g in range(G)]
+        res.append(out)
+        sw.close()
+    for x, y in zip(*res):
+        _close(x, y, atol=1e-13)
