@@ -829,6 +829,19 @@ SweepFn pick_kernel(int np, int tally)
     return nullptr;
 }
 
+typedef void (*CacheFn)(const CacheArgs);
+
+CacheFn pick_cache_kernel(int np)
+{
+    switch (np) {
+    case 1: return exp_cache_kernel<1>;
+    case 2: return exp_cache_kernel<2>;
+    case 3: return exp_cache_kernel<3>;
+    case 4: return exp_cache_kernel<4>;
+    }
+    return nullptr;
+}
+
 typedef void (*WarpFn)(const WarpArgs);
 
 template <int GL, bool CACHED> WarpFn pick_warp_gl(int np, int tally)
@@ -1065,7 +1078,8 @@ int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb
                 e = cudaFuncSetAttribute((const void *)pick_chunk_kernel(np, nw, t),
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kChunkSmemBudget);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute((const void *)exp_cache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int np = 1; np <= kMaxPolar && e == cudaSuccess; np++)
+            e = cudaFuncSetAttribute((const void *)pick_cache_kernel(np), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
         fail(nullptr, MOCB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         mocb200_destroy(h);
@@ -1296,7 +1310,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 c.exp_table = h->d_exp, c.exp_n = h->exp_n, c.exp_min = h->exp_min, c.exp_max = h->exp_max;
                 const int64_t warps = (int64_t)tl.n_units * tl.n_planes;
                 const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((warps + 15) / 16, h->sm_count));
-                exp_cache_kernel<<<grid, 512, smem, h->stream>>>(c);
+                pick_cache_kernel(tl.np)<<<grid, 512, smem, h->stream>>>(c);
                 h->stats.kernel_launches++;
             }
             for (int g = g_begin; g < g_begin + g_count; g++)

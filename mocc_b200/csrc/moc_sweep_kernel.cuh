@@ -674,7 +674,7 @@ struct CacheArgs {
     double exp_min, exp_max;
 };
 
-__global__ void __launch_bounds__(512, 1) exp_cache_kernel(const CacheArgs a)
+template <int P> __global__ void __launch_bounds__(512, 1) exp_cache_kernel(const CacheArgs a)
 {
     extern __shared__ __align__(16) double s_tab[];
     for (int i = threadIdx.x; i < a.exp_n + 2; i += blockDim.x)
@@ -686,7 +686,6 @@ __global__ void __launch_bounds__(512, 1) exp_cache_kernel(const CacheArgs a)
     const int lane      = threadIdx.x & 31;
     const int warps     = gridDim.x * (blockDim.x >> 5);
     const int64_t total = (int64_t)a.n_units * a.n_planes;
-    const int P         = a.np;
     for (int64_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += warps) {
         const int unit_id   = (int)(w / a.n_planes);
         const int ipl       = (int)(w - (int64_t)unit_id * a.n_planes);
@@ -695,24 +694,41 @@ __global__ void __launch_bounds__(512, 1) exp_cache_kernel(const CacheArgs a)
         const TrackUnit u   = a.units[unit_id];
         const int4 lb4      = a.len_begin[unit_id];
         const int lb[4]     = {lb4.x, lb4.y, lb4.z, lb4.w};
-        const int npad      = (u.nseg + 3) & ~3;
+        double nrs[P];
+#pragma unroll
+        for (int p = 0; p < P; p++)
+            nrs[p] = -a.ang_rsintheta[a.bundles[u.bundle].ang[p]];
+        const int npad = (u.nseg + 3) & ~3;
         for (int k = lane; k < npad; k += 32) {
             const bool valid = k < u.nseg;
             const int reg    = a.seg_fsr[u.seg_begin + k] + first_reg;
+            double len[P]; // every polar angle has its own lengths (polar copies may differ in the last bits)
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                len[p] = a.seg_len[lb[p] + k];
             for (int gi = 0; gi < a.g_count; gi++) {
                 const int g     = a.g_begin + gi;
                 const double xs = a.xstr[(size_t)reg * a.GP + g];
-                for (int p = 0; p < P; p++) {
-                    // every polar angle has its own lengths (polar copies may differ in the last bits)
-                    const double t   = xs * a.seg_len[lb[p] + k];
-                    const double nrs = -a.ang_rsintheta[a.bundles[u.bundle].ang[p]];
-                    const double ex  = valid ? exp_interp(s_tab, t * nrs, c0, rspace) : 1.0;
-                    size_t o;
-                    if (a.group_major)
-                        o = (((size_t)ipl * a.cache_groups + (g - a.cache_g0)) * a.list_pseg + u.cpos + k) * P + p;
-                    else
-                        o = (((size_t)ipl * a.list_pseg + u.cpos + k) * P + p) * a.GP + g;
-                    a.cache[o] = ex;
+                double ex[P];
+#pragma unroll
+                for (int p = 0; p < P; p++)
+                    ex[p] = valid ? exp_interp(s_tab, xs * len[p] * nrs[p], c0, rspace) : 1.0;
+                if (a.group_major) { // [plane][g][pos][P]: the P values of a position are contiguous
+                    double *dst = a.cache + (((size_t)ipl * a.cache_groups + (g - a.cache_g0)) * a.list_pseg + u.cpos + k) * P;
+                    if constexpr (P == 2) {
+                        *reinterpret_cast<double2 *>(dst) = make_double2(ex[0], ex[1]);
+                    } else if constexpr (P == 4) {
+                        *reinterpret_cast<double2 *>(dst)     = make_double2(ex[0], ex[1]);
+                        *reinterpret_cast<double2 *>(dst + 2) = make_double2(ex[2], ex[3]);
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < P; p++)
+                            dst[p] = ex[p];
+                    }
+                } else { // [plane][pos][P][GP]
+#pragma unroll
+                    for (int p = 0; p < P; p++)
+                        a.cache[(((size_t)ipl * a.list_pseg + u.cpos + k) * P + p) * a.GP + g] = ex[p];
                 }
             }
         }
