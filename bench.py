@@ -92,6 +92,17 @@ def workload_files(name="c5g7_2d"):
     return flat
 
 
+L2_NOTE = ("working set per step (segment + attenuation streams, > 1 GB) exceeds the 126 MB L2 and every host cache; "
+           "the B200 arm also writes a 256 MB flush buffer between timed steps")
+
+
+def workload_config(name, mode, boundary, S, n_reg, G, n_inner, world):
+    """`config` of the JSON line: the WORKLOAD only, identical for the B200 arm and the reference arm."""
+    return {"workload": WORKLOADS[name][0] + (f"; {world} axial planes, one per GPU" if world > 1 else ""),
+            "mode": mode, "boundary_update": boundary, "segments": int(S), "n_reg": int(n_reg), "groups": int(G),
+            "n_inner": int(n_inner), "updates_per_step": 2.0 * S * G * n_inner * world, "l2": L2_NOTE}
+
+
 def synthetic_source(arr, G, n_reg):
     """Fixed one-group sources from a flat unit flux: fission (k = 1) + in-scatter; synthetic."""
     nf, ch, scat = arr["xs_nf"], arr["xs_ch"], arr["xs_scat"]
@@ -153,24 +164,37 @@ def run_reference(args):
     if not os.path.exists(REF_TOOL):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_tool not built"}))
         return
+    # Same workload as the B200 arm: the XML's n_inner (10) is NEVER changed, so the share of tallying
+    # (moc::Current) inners is the same 1 in 10. The run is bounded instead by sweeping only the first
+    # `ng` of the 7 groups in every step when K + W full steps would exceed the CPU-time budget (every
+    # group costs the same: same rays, same inners); updates are counted for the groups actually swept.
     total = args.steps + args.warmup
-    n_inner = max(1, min(10, 30 // max(total, 1)))
+    G, n_inner = 7, 10
+    est_full_step_s = 2.55e9 / (9.0e7 * min(cores, 16))  # ~9e7 updates/s per host thread (r1 measurement)
+    budget_s = float(os.environ.get("MOCC_B200_REF_BUDGET_S", "150"))
+    ng = int(max(1, min(G, budget_s / (total * est_full_step_s) * G)))
     inputs = os.path.join(ROOT, "oracle", "_ref", "inputs")
     env = dict(os.environ, OMP_NUM_THREADS=str(cores))
     cmd = [REF_TOOL, "time", "c5g7_2d.xml", "--cmfd", "--sweeps", str(args.steps), "--warmup", str(args.warmup),
-           "--set", f"solver/sweeper@n_inner={n_inner}"]
+           "--groups", str(ng)]
     out = subprocess.run(cmd, cwd=inputs, env=env, capture_output=True, text=True, check=True).stdout
     res = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+    assert res["n_inner"] == n_inner, "reference arm must run the XML's n_inner"
     value = res["updates_per_s"]
-    sample = (f"{args.steps} passes of c5g7_2d.xml: 7 groups x {n_inner} inner sweeps each (last inner with the "
-              f"moc::Current tally), {res['updates']:.3e} updates in {res['seconds']:.2f} s")
+    sample = (f"{args.steps} timed steps (+{args.warmup} warm-up) of c5g7_2d.xml, each {res['groups']} of 7 groups x "
+              f"{n_inner} inner sweeps (last inner with the moc::Current tally), {res['updates']:.3e} updates in "
+              f"{res['seconds']:.2f} s")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] / args.steps * 1e3,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] / args.steps * 1e3 * G / res["groups"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "examples/c5g7_2d.xml geometry and cross sections, flat initial flux",
-        "config": {"workload": "C5G7 2-D (examples/c5g7_2d.xml), reference MoCSweeper on CPU", "n_inner": n_inner,
-                   "threads": res["threads"]},
+        # the same `config` object as the B200 arm prints for this workload (implementation details of either arm
+        # live in `arm`, not in `config`)
+        "config": dict(workload_config("c5g7_2d", "pergroup", "gs", res["segments"], res["n_reg"], G, n_inner, 1),
+                       **({"groups_sampled_per_step": res["groups"]} if res["groups"] != G else {})),
+        "arm": {"sweeper": "reference MoCSweeper on CPU (OpenMP), unmodified sources (oracle/_ref)",
+                "threads": res["threads"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -367,13 +391,9 @@ def main():
             "vs_baseline": None, "dtype": "f64",
             "data": "examples/c5g7_2d.xml geometry and cross sections (flattened on the box); synthetic fixed "
                     "source (fission + in-scatter of a flat unit flux)",
-            "config": {"workload": WORKLOADS[args.workload][0] +
-                                   (f"; {world} axial planes, one per GPU" if world > 1 else ""),
-                       "mode": args.mode, "boundary_update": args.boundary, "segments": S, "resident_segments": n_useg,
-                       "n_reg": n_reg, "groups": G, "n_inner": n_inner, "updates_per_step": updates_step,
-                       "l2": "256 MB flush write between timed steps; device-resident inputs 450 MB > 126 MB L2",
-                       "kernel": kname, "bundled_segments": int(st["swept_segments"]), "max_polar": args.max_polar or 2,
-                       "cache_groups": args.cache_groups or G},
+            "config": workload_config(args.workload, args.mode, args.boundary, S, n_reg, G, n_inner, world),
+            "arm": {"kernel": kname, "resident_segments": n_useg, "bundled_segments": int(st["swept_segments"]),
+                    "max_polar": args.max_polar or 2, "cache_groups": args.cache_groups or G},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(ln.item()),
             "clocks": clocks,

@@ -370,7 +370,7 @@ int main(int argc, char **argv)
         std::string cmd = argv[1], xml = argv[2];
         std::string out_path;
         std::vector<std::string> sets;
-        int outers = 1, sweeps = 2, warmup = 1;
+        int outers = 1, sweeps = 2, warmup = 1, groups_limit = 0;
         bool cmfd = false, twod3d = false;
         std::string records;
         for (int i = 3; i < argc; i++) {
@@ -385,6 +385,8 @@ int main(int argc, char **argv)
                 warmup = std::atoi(argv[++i]);
             else if (a == "--records" && i + 1 < argc)
                 records = argv[++i];
+            else if (a == "--groups" && i + 1 < argc)
+                groups_limit = std::atoi(argv[++i]);
             else if (a == "--cmfd")
                 cmfd = true;
             else if (a == "--2d3d")
@@ -475,8 +477,11 @@ int main(int argc, char **argv)
             sw.initialize();
             ArrayB1 fs(sw.n_reg());
             sw.calc_fission_source(1.0, fs);
+            // --groups N: a bounded sample, the first N groups of every pass (all groups cost the same:
+            // same rays, same n_inner, same share of tallying inners)
+            const int ng_pass = (groups_limit > 0 && groups_limit < ng) ? groups_limit : ng;
             auto pass = [&]() {
-                for (int ig = 0; ig < ng; ig++) {
+                for (int ig = 0; ig < ng_pass; ig++) {
                     source->initialize_group(ig);
                     source->fission(fs, ig);
                     source->in_scatter(ig);
@@ -489,11 +494,11 @@ int main(int argc, char **argv)
             for (int i = 0; i < sweeps; i++)
                 pass();
             double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            double updates = 2.0 * (double)S * ng * sw.n_inner() * sweeps;
-            std::printf("{\"impl\": \"reference\", \"segments\": %lld, \"groups\": %d, \"n_inner\": %d, "
+            double updates = 2.0 * (double)S * ng_pass * sw.n_inner() * sweeps;
+            std::printf("{\"impl\": \"reference\", \"segments\": %lld, \"n_reg\": %d, \"groups\": %d, \"n_inner\": %d, "
                         "\"passes\": %d, \"updates\": %.0f, \"seconds\": %.6f, \"updates_per_s\": %.6e, "
                         "\"threads\": %d, \"current_tally\": %s}\n",
-                        (long long)S, ng, sw.n_inner(), sweeps, updates, secs, updates / secs,
+                        (long long)S, (int)sw.n_reg(), ng_pass, sw.n_inner(), sweeps, updates, secs, updates / secs,
                         omp_get_max_threads(), cmfd ? "true" : "false");
             return 0;
         }
