@@ -379,11 +379,11 @@ def main():
                              f"(OpenMP, unmodified sources in oracle/_ref)"}
 
     st = sw.stats()
-    kname = {1: "item", 2: "track", 3: "cached", 4: "chunk"}.get(int(st["kernel"]), "?")
-    if args.mode == "batched" and kname == "chunk":
+    kname = {1: "item", 2: "track", 3: "cached", 4: "chunk", 5: "rchunk"}.get(int(st["kernel"]), "?")
+    if args.mode == "batched" and kname in ("chunk", "rchunk"):
         kname = "cached"  # group-batched sweeps run the 8-group-lane warp kernel on the same cache
     kfunc = {"item": "sweep_kernel", "track": "sweep_warp_kernel<CACHED=false>", "cached": "sweep_warp_kernel<CACHED=true>",
-             "chunk": "sweep_chunk_kernel"}[kname]
+             "chunk": "sweep_chunk_kernel", "rchunk": "sweep_rchunk_kernel"}[kname]
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -63,11 +63,13 @@ extern "C" {
                                   factor tables (<= 2 ulp from the table entries) */
 
 /* sweep kernel selection (diagnostics / A-B measurements) */
-#define MOCB200_KERNEL_AUTO 0   /* CHUNK when the attenuation cache fits in device memory, else TRACK */
+#define MOCB200_KERNEL_AUTO 0   /* RCHUNK when the attenuation cache fits in device memory, else TRACK */
 #define MOCB200_KERNEL_ITEM 1   /* one thread per (track, direction, group), serial walk */
 #define MOCB200_KERNEL_TRACK 2  /* one warp per track, both directions, affine scan over lanes */
 #define MOCB200_KERNEL_CACHED 3 /* TRACK with the table lookups cached in HBM per cross-section upload */
 #define MOCB200_KERNEL_CHUNK 4  /* CACHED with one scan per track: TMA-staged track, lane-owned contiguous chunks */
+#define MOCB200_KERNEL_RCHUNK 5 /* CHUNK, second generation: register-resident chunks of fixed length packed into
+                                   equal batches, one lane per (chunk, polar angle), one scan per batch */
 
 /*
  * Flattened ray-tracing data ("MOCFLAT"), produced once on the host from the

@@ -18,7 +18,7 @@ MAX_POLAR = 4
 TALLY_NONE, TALLY_CURRENT, TALLY_CORRECTIONS = 0, 1, 2
 BOUNDARY_GS, BOUNDARY_JACOBI = 0, 1
 EXP_TABLE, EXP_FACTORED = 0, 1
-KERNEL_AUTO, KERNEL_ITEM, KERNEL_TRACK, KERNEL_CACHED = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_ITEM, KERNEL_TRACK, KERNEL_CACHED, KERNEL_CHUNK, KERNEL_RCHUNK = 0, 1, 2, 3, 4, 5
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)

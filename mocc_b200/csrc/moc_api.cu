@@ -16,6 +16,7 @@
 #include "moc_kernels.cuh"
 #include "moc_sweep_kernel.cuh"
 #include "moc_chunk_kernel.cuh"
+#include "moc_rchunk_kernel.cuh"
 
 using namespace mocb200;
 
@@ -26,6 +27,16 @@ thread_local std::string g_create_error;
 struct DeviceBuf {
     void *p      = nullptr;
     size_t bytes = 0;
+};
+
+// Register-chunk kernel (moc_rchunk_kernel.cuh): the tracks of a list cut into chunks of LMAX slots and packed into
+// batches of NC chunks; a unit is what one team sweeps (one batch, or the consecutive batches of one long track)
+struct RcList {
+    int P = 0, LMAX = 0, NW = 0, TEAMS = 0, NC = 0, NS = 0;
+    int64_t n_slots = 0; // n_batches * NS: positions of the list's attenuation cache per (plane, group)
+    int32_t n_batches = 0, n_units = 0, max_nb = 1;
+    int2 *d_units = nullptr, *d_lane_meta = nullptr, *d_bc_slots = nullptr, *d_chunk_trk = nullptr;
+    int32_t *d_slot_fsr = nullptr;
 };
 
 struct TrackList { // one launch of the track kernel: units of one (unique plane, boundary phase, polar count)
@@ -42,6 +53,8 @@ struct TrackList { // one launch of the track kernel: units of one (unique plane
     int4 *d_len_begin   = nullptr; // per unit and polar angle: start of that angle's own segment lengths
     std::vector<int32_t> nseg_desc; // track lengths, longest first (staging-cap choice of the chunk kernel)
     double *d_cache    = nullptr; // attenuation cache of this list (CACHED kernel)
+    RcList rc;                    // register-chunk kernel: packed batches
+    int64_t cache_positions(bool rchunk) const { return rchunk ? rc.n_slots : pseg; }
 };
 
 struct WorkList { // one kernel launch: items of one (unique plane, boundary phase, polar count)
@@ -121,6 +134,7 @@ struct mocb200_sweeper {
     double2 *d_xq = nullptr;
     double *d_scratch = nullptr;
     int scratch_per_warp = 0;
+    int rc_scratch_per_team = 0;
     int max_nseg = 0;
     int track_grid = 0;
     std::vector<bool> have_xs;
@@ -226,6 +240,141 @@ void build_crossings(const mocb200_problem &p, int64_t t, int nseg, std::vector<
     }
 }
 
+// ---- register-chunk kernel: launch geometry and batch packing ----
+bool rc_config_known(const RcConfig &c)
+{
+    return pick_rc_kernel_p2(0, c) != nullptr;
+}
+
+// default: long chunks while the longest track still fits one batch, else the chained path takes the few longest
+RcConfig rc_pick_config(int np, int max_nseg)
+{
+    static const char *force = getenv("MOCB200_RC_CFG"); // tuning hook: "LMAX,NW,TEAMS"
+    if (force) {
+        RcConfig c{0, 0, 0};
+        if (sscanf(force, "%d,%d,%d", &c.LMAX, &c.NW, &c.TEAMS) == 3 && rc_config_known(c))
+            return c;
+    }
+    (void)np;
+    (void)max_nseg;
+    return RcConfig{11, 4, 4};
+}
+
+// Cuts the tracks of a list (cu: longest first) into chunks of LMAX slots and packs them into batches of NC
+// chunks such that no track straddles a batch (best fit, decreasing); a track with more than NC chunks takes
+// consecutive batches of its own (chained unit). Uploads the per-slot / per-lane tables the kernel reads.
+int build_rc_list(mocb200_sweeper *h, TrackList &tl, const std::vector<ChunkUnit> &cu, const std::vector<int32_t> &pfsr)
+{
+    RcList &rc = tl.rc;
+    const RcConfig cfg = rc_pick_config(tl.np, tl.max_nseg);
+    rc.P = tl.np, rc.LMAX = cfg.LMAX, rc.NW = cfg.NW, rc.TEAMS = cfg.TEAMS;
+    rc.NC = rc_chunks(rc.P, rc.NW), rc.NS = rc.NC * rc.LMAX;
+    const int NC = rc.NC, L = rc.LMAX, P = rc.P;
+    // chunks a batch may hold: NC; the chunk_cap test hook lowers it (the rest of every batch stays empty) so
+    // that small test problems exercise the chained path
+    int NCp = NC;
+    if (h->opt.chunk_cap != 0)
+        NCp = std::max(2, std::min(NC, std::abs(h->opt.chunk_cap) / L));
+    struct Placed {
+        int unit, batch, chunk0, nch;
+    };
+    std::vector<Placed> placed;
+    std::vector<int2> units;
+    int n_batches = 0;
+    std::vector<int> nch(cu.size());
+    for (size_t i = 0; i < cu.size(); i++)
+        nch[i] = std::max(2, (cu[i].nseg + L - 1) / L); // >= 2: head and tail never share a chunk
+    // chained units first (they are the longest tracks): consecutive batches of their own
+    for (size_t i = 0; i < cu.size(); i++) {
+        if (nch[i] <= NCp)
+            continue;
+        const int nb = (nch[i] + NCp - 1) / NCp;
+        if (nch[i] - (nb - 1) * NCp < 2) // every sub-block needs a first and a last chunk of its own
+            nch[i] = (nb - 1) * NCp + 2;
+        placed.push_back({(int)i, n_batches, 0, nch[i]});
+        units.push_back(make_int2(n_batches, nb));
+        n_batches += nb;
+        rc.max_nb = std::max(rc.max_nb, nb);
+    }
+    // the rest: best fit into the open batches (open_by_room[r]: batches with r free chunks)
+    std::vector<std::vector<int>> open_by_room(NCp + 1);
+    std::vector<int> used; // chunks used per normal batch (indexed from first_normal)
+    const int first_normal = n_batches;
+    for (size_t i = 0; i < cu.size(); i++) {
+        if (nch[i] > NCp)
+            continue;
+        int r = nch[i];
+        while (r <= NCp && open_by_room[r].empty())
+            r++;
+        int b;
+        if (r > NCp) {
+            b = (int)used.size();
+            used.push_back(0);
+            r = NCp;
+        } else {
+            b = open_by_room[r].back();
+            open_by_room[r].pop_back();
+        }
+        placed.push_back({(int)i, first_normal + b, used[b], nch[i]});
+        used[b] += nch[i];
+        if (r - nch[i] > 0)
+            open_by_room[r - nch[i]].push_back(b);
+    }
+    for (size_t b = 0; b < used.size(); b++)
+        units.push_back(make_int2(first_normal + (int)b, 1));
+    n_batches += (int)used.size();
+    rc.n_batches = n_batches, rc.n_units = (int32_t)units.size();
+    rc.n_slots   = (int64_t)n_batches * rc.NS;
+    if (rc.n_slots >= (int64_t)INT32_MAX)
+        return fail(h, MOCB200_ERR_INVALID, "register-chunk kernel: slot count exceeds 32-bit indexing");
+
+    std::vector<int32_t> slot_fsr((size_t)rc.n_slots, -1);
+    std::vector<int2> chunk_trk((size_t)n_batches * NC, make_int2(-1, 0));
+    std::vector<int2> lane_meta((size_t)n_batches * NC * P, make_int2(0, 0));
+    std::vector<int2> bc_slots;
+    for (const Placed &pl : placed) {
+        const ChunkUnit &u = cu[pl.unit];
+        const bool chained = pl.nch > NCp;
+        for (int j = 0; j < pl.nch; j++) {
+            // chained units: sub-block j / NCp, chunk j % NCp of it
+            const int in_batch = chained ? j % NCp : pl.chunk0 + j;
+            const int gchunk   = (pl.batch + (chained ? j / NCp : 0)) * NC + in_batch;
+            const int k0       = j * L;
+            chunk_trk[gchunk]  = make_int2(pl.unit, k0);
+            for (int k = 0; k < L && k0 + k < u.nseg; k++)
+                slot_fsr[(size_t)gchunk * L + k] = pfsr[(size_t)u.seg_begin + k0 + k];
+            int flags = 0;
+            if (j == 0)
+                flags |= kRcHead;
+            else if (chained && in_batch == 0)
+                flags |= kRcHeadCont;
+            if (j == pl.nch - 1)
+                flags |= kRcTail;
+            else if (chained && in_batch == NCp - 1)
+                flags |= kRcTailCont;
+            for (int q = 0; q < P; q++) {
+                int2 m = make_int2(flags | (u.ang[q] << 8), 0);
+                if (flags & kRcHead) {
+                    m.y = (int)bc_slots.size();
+                    bc_slots.push_back(make_int2(u.in_f[q], u.out_b[q]));
+                } else if (flags & kRcTail) {
+                    m.y = (int)bc_slots.size();
+                    bc_slots.push_back(make_int2(u.in_b[q], u.out_f[q]));
+                }
+                lane_meta[(size_t)gchunk * P + q] = m;
+            }
+        }
+    }
+    if (bc_slots.empty())
+        bc_slots.push_back(make_int2(0, INT32_MIN));
+    int rc2;
+    if ((rc2 = dev_upload(h, &rc.d_units, units)) || (rc2 = dev_upload(h, &rc.d_lane_meta, lane_meta)) ||
+        (rc2 = dev_upload(h, &rc.d_bc_slots, bc_slots)) || (rc2 = dev_upload(h, &rc.d_chunk_trk, chunk_trk)) ||
+        (rc2 = dev_upload(h, &rc.d_slot_fsr, slot_fsr)))
+        return rc2;
+    return MOCB200_OK;
+}
+
 int validate(const mocb200_problem *p)
 {
     if (!p)
@@ -274,9 +423,10 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
 
     // ---- kernel selection: the attenuation cache needs 8 bytes per (padded segment, polar angle, group, plane) ----
     h->kernel = opt.kernel;
-    if (h->kernel < MOCB200_KERNEL_AUTO || h->kernel > MOCB200_KERNEL_CHUNK)
+    if (h->kernel < MOCB200_KERNEL_AUTO || h->kernel > MOCB200_KERNEL_RCHUNK)
         return fail(h, MOCB200_ERR_INVALID, "unknown kernel selection %d", h->kernel);
-    if (h->kernel == MOCB200_KERNEL_AUTO || h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK) {
+    if (h->kernel == MOCB200_KERNEL_AUTO || h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK ||
+        h->kernel == MOCB200_KERNEL_RCHUNK) {
         int64_t bytes = 0;
         for (int u = 0; u < p.n_unique; u++) {
             int64_t n_planes_u = 0;
@@ -301,10 +451,10 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
         if (!fits && h->kernel != MOCB200_KERNEL_AUTO)
             return fail(h, MOCB200_ERR_INVALID, "attenuation cache (%lld MiB per group) does not fit in device memory",
                         (long long)((bytes / h->G) >> 20));
-        h->kernel = !fits ? MOCB200_KERNEL_TRACK
-                          : (h->kernel == MOCB200_KERNEL_CACHED ? MOCB200_KERNEL_CACHED : MOCB200_KERNEL_CHUNK);
+        h->kernel = !fits ? MOCB200_KERNEL_TRACK : (h->kernel == MOCB200_KERNEL_AUTO ? MOCB200_KERNEL_RCHUNK : h->kernel);
     }
-    const bool cached_build = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK;
+    const bool cached_build = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK ||
+                              h->kernel == MOCB200_KERNEL_RCHUNK;
 
     // ---- topology classes of the geometry classes ----
     // The reference keeps one ray set per (azimuth, polar) angle; polar copies of an azimuth visit the same
@@ -373,6 +523,13 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     };
     make_bundles(false, bundles, bundle_phase, bundle_geom);
     make_bundles(true, tbundles, tbundle_phase, tbundle_geom);
+    if (h->kernel == MOCB200_KERNEL_RCHUNK) { // one lane per polar angle: bundles of 1, 2 or 4; 8-bit flags + angle in 32 bits
+        bool ok = p.n_ang < (1 << 23);
+        for (const auto &b : tbundles)
+            ok = ok && b.np != 3;
+        if (!ok)
+            h->kernel = MOCB200_KERNEL_CHUNK;
+    }
 
     // ---- crossing lists, one pair per track ----
     std::vector<Cross> cross;
@@ -611,6 +768,8 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                             pinfo.push_back(make_int2(ip, p.plane_first_reg[ip]));
                         if ((rc2 = dev_upload(h, &tl.d_cunits, cu)) || (rc2 = dev_upload(h, &tl.d_pinfo, pinfo)))
                             return rc2;
+                        if (h->kernel == MOCB200_KERNEL_RCHUNK && (rc2 = build_rc_list(h, tl, cu, pfsr)))
+                            return rc2;
                     }
                     h->tlists.push_back(tl);
                 }
@@ -618,7 +777,10 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
         }
         h->track_grid       = h->sm_count;
         h->scratch_per_warp = (h->max_nseg / 16 + 1) * 8 * kMaxPolar;
-        const size_t n_sc   = (size_t)h->track_grid * (kWarpBlock / 32) * h->scratch_per_warp;
+        for (const auto &tl : h->tlists)
+            h->rc_scratch_per_team = std::max(h->rc_scratch_per_team, (tl.rc.max_nb + 1) * kMaxPolar);
+        const size_t n_sc   = std::max((size_t)h->track_grid * (kWarpBlock / 32) * h->scratch_per_warp,
+                                       (size_t)h->track_grid * 8 * h->rc_scratch_per_team);
         if ((rc2 = dev_alloc(h, &h->d_scratch, n_sc)))
             return rc2;
     }
@@ -896,6 +1058,29 @@ ChunkFn pick_chunk_kernel(int np, int nw, int tally)
     return nullptr;
 }
 
+typedef void (*RcCacheFn)(const RcCacheArgs);
+
+// the instantiations live in moc_rc_p{1,2,4}.cu (one translation unit per lane count, compiled in parallel)
+RcFn pick_rc_kernel(int np, int tally, const RcConfig &c)
+{
+    switch (np) {
+    case 1: return pick_rc_kernel_p1(tally, c);
+    case 2: return pick_rc_kernel_p2(tally, c);
+    case 4: return pick_rc_kernel_p4(tally, c);
+    }
+    return nullptr;
+}
+
+RcCacheFn pick_rc_cache_kernel(int np)
+{
+    switch (np) {
+    case 1: return rc_cache_kernel<1>;
+    case 2: return rc_cache_kernel<2>;
+    case 4: return rc_cache_kernel<4>;
+    }
+    return nullptr;
+}
+
 constexpr int kChunkSmemBudget = 232448 - 12800; // opt-in dynamic shared memory per CTA minus the static part
 
 // launch geometry of the chunk kernel for a list: segments a team stages at once, warps per team,
@@ -1080,6 +1265,17 @@ int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb
     if (e == cudaSuccess)
         for (int np = 1; np <= kMaxPolar && e == cudaSuccess; np++)
             e = cudaFuncSetAttribute((const void *)pick_cache_kernel(np), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (h->kernel == MOCB200_KERNEL_RCHUNK) {
+        for (const auto &tl : h->tlists) {
+            const RcList &rc = tl.rc;
+            const RcConfig cfg{rc.LMAX, rc.NW, rc.TEAMS};
+            for (int t = 0; t < 3 && e == cudaSuccess; t++)
+                e = cudaFuncSetAttribute((const void *)pick_rc_kernel(rc.P, t, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(rc.TEAMS * rc_team_bytes(rc.P, rc.LMAX, rc.NW)));
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute((const void *)pick_rc_cache_kernel(rc.P), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        }
+    }
     if (e != cudaSuccess) {
         fail(nullptr, MOCB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         mocb200_destroy(h);
@@ -1262,8 +1458,10 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
 
     const int gl          = g_count <= 2 ? 1 : 8; // group lanes per segment (track / cached kernels)
     const int n_gsets     = (g_count + gl - 1) / gl;
-    const bool cached     = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK;
+    const bool cached     = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK ||
+                            h->kernel == MOCB200_KERNEL_RCHUNK;
     const bool group_major = cached && gl == 1;
+    const bool rchunk      = h->kernel == MOCB200_KERNEL_RCHUNK && gl == 1; // packed-batch layout of the cache
 
     if (cached && gl != 1 && h->cache_slots < h->G)
         return fail(h, MOCB200_ERR_STATE, "group-batched sweeps need the attenuation cache of all groups (%d of %d fit)",
@@ -1278,10 +1476,11 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 if (tl.d_cache) {
                     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
                     CUDA_TRY(h, cudaFree(tl.d_cache));
-                    h->device_bytes -= tl.pseg * tl.np * tl.n_planes * (int64_t)(h->cache_layout == 1 ? h->cache_slots : h->GP) * 8;
+                    h->device_bytes -= tl.cache_positions(h->kernel == MOCB200_KERNEL_RCHUNK && h->cache_layout == 1) * tl.np *
+                                       tl.n_planes * (int64_t)(h->cache_layout == 1 ? h->cache_slots : h->GP) * 8;
                     tl.d_cache = nullptr;
                 }
-                const size_t bytes = (size_t)tl.pseg * tl.np * tl.n_planes * (gl == 1 ? h->cache_slots : h->GP) * 8;
+                const size_t bytes = (size_t)tl.cache_positions(rchunk) * tl.np * tl.n_planes * (gl == 1 ? h->cache_slots : h->GP) * 8;
                 CUDA_TRY(h, cudaMalloc((void **)&tl.d_cache, bytes));
                 h->device_bytes += (int64_t)bytes;
             }
@@ -1298,6 +1497,21 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
             dirty = dirty || !h->cache_valid[g];
         if (dirty) {
             for (const auto &tl : h->tlists) {
+                if (rchunk) {
+                    RcCacheArgs c{};
+                    c.chunk_trk = tl.rc.d_chunk_trk, c.tracks = tl.d_cunits, c.len_begin = tl.d_len_begin;
+                    c.planes = tl.d_planes, c.n_planes = tl.n_planes, c.lmax = tl.rc.LMAX, c.n_slots = tl.rc.n_slots;
+                    c.seg_len = h->d_pseg_len, c.seg_fsr = h->d_pseg_fsr, c.ang_rsintheta = h->d_rsin;
+                    c.plane_first_reg = h->d_plane_first_reg, c.xstr = h->d_xstr;
+                    c.g_begin = g_begin, c.g_count = g_count, c.cache_groups = h->cache_slots;
+                    c.cache_g0 = sliding ? g_begin : 0, c.GP = h->GP, c.cache = tl.d_cache;
+                    c.exp_table = h->d_exp, c.exp_n = h->exp_n, c.exp_min = h->exp_min, c.exp_max = h->exp_max;
+                    const int grid = (int)std::max<int64_t>(
+                        1, std::min<int64_t>((tl.rc.n_slots * tl.n_planes + 511) / 512, (int64_t)h->sm_count));
+                    pick_rc_cache_kernel(tl.np)<<<grid, 512, smem, h->stream>>>(c);
+                    h->stats.kernel_launches++;
+                    continue;
+                }
                 CacheArgs c{};
                 c.units = tl.d_units, c.n_units = tl.n_units, c.bundles = h->d_tbundles, c.len_begin = tl.d_len_begin;
                 c.planes = tl.d_planes, c.n_planes = tl.n_planes;
@@ -1441,7 +1655,29 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 a.cache = tl.d_cache, a.list_pseg = tl.pseg, a.cache_groups = h->cache_slots;
                 a.cache_g0 = sliding ? g_begin : 0;
                 a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
-                if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1) {
+                if (rchunk) {
+                    const RcList &rc = tl.rc;
+                    const RcConfig cfg{rc.LMAX, rc.NW, rc.TEAMS};
+                    RcFn fn = pick_rc_kernel(rc.P, tally, cfg);
+                    if (!fn)
+                        return fail(h, MOCB200_ERR_INVALID, "register-chunk kernel: no instantiation for P %d tally %d (%d,%d,%d)",
+                                    rc.P, tally, rc.LMAX, rc.NW, rc.TEAMS);
+                    RcArgs c{};
+                    c.units = rc.d_units, c.n_units = rc.n_units, c.pinfo = tl.d_pinfo, c.n_planes = tl.n_planes;
+                    c.lane_meta = rc.d_lane_meta, c.bc_slots = rc.d_bc_slots, c.chunk_trk = rc.d_chunk_trk;
+                    c.tracks = tl.d_cunits, c.slot_fsr = rc.d_slot_fsr, c.cache = tl.d_cache, c.n_slots = rc.n_slots;
+                    c.cache_groups = h->cache_slots, c.cache_g0 = sliding ? g_begin : 0;
+                    c.wt_v_st = h->d_wt, c.n_ang = h->n_ang, c.bc_per_group = h->bcpg;
+                    c.g_begin = g_begin, c.g_count = g_count, c.GP = h->GP, c.n_reg = h->n_reg;
+                    c.q = h->d_qg, c.tally = h->d_tg, c.bc_in = bc_in, c.bc_out = bc_out;
+                    c.scratch = h->d_scratch, c.scratch_per_team = h->rc_scratch_per_team;
+                    c.cross = h->d_xcross, c.cur_w = h->d_curw, c.flx_w = h->d_flxw;
+                    c.plane_surf_offset = h->d_plane_surf_offset, c.current = h->d_current, c.surface_flux = h->d_surfflux;
+                    c.dsum = h->d_dsum, c.ssum = h->d_ssum, c.n_surf_plane = h->n_surf_plane, c.n_plane_total = h->n_plane;
+                    const int64_t items = (int64_t)rc.n_units * tl.n_planes * g_count;
+                    const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>((items + rc.TEAMS - 1) / rc.TEAMS, h->sm_count));
+                    fn<<<rgrid, 32 * rc.NW * rc.TEAMS, rc.TEAMS * rc_team_bytes(rc.P, rc.LMAX, rc.NW), h->stream>>>(c);
+                } else if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1) {
                     int caps = 0, nw = 1, teams = 1;
                     const bool tl_tally = tally != MOCB200_TALLY_NONE;
                     chunk_geometry(tl.nseg_desc, tl.np, h->opt.chunk_cap, tl_tally, &caps, &nw, &teams);

@@ -111,7 +111,7 @@ __device__ __forceinline__ double exp_table_lookup(const double *__restrict__ ta
 }
 
 template <int P, int TALLY>
-__global__ void __launch_bounds__(512, 2) sweep_kernel(const SweepArgs a)
+static __global__ void __launch_bounds__(512, 2) sweep_kernel(const SweepArgs a)
 {
     extern __shared__ double s_tab[];
     for (int i = threadIdx.x; i < a.exp_n + 2; i += blockDim.x)
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(512, 2) sweep_kernel(const SweepArgs a)
 
 // q-bar = (src + flux*xs_self) * (1/(xstr_src*4pi)); also clears the sweep tally.
 // Non-contracted arithmetic: bit-identical to source_isotropic.cpp:29-31.
-__global__ void self_scatter_kernel(int n_reg, int GP, int g_begin, int g_count, const double *__restrict__ src,
+static __global__ void self_scatter_kernel(int n_reg, int GP, int g_begin, int g_count, const double *__restrict__ src,
                                     const double *__restrict__ flux, const double *__restrict__ xs_self,
                                     const double *__restrict__ xstr_src, double *__restrict__ qbar,
                                     double *__restrict__ tally, int compute_q)
@@ -303,7 +303,7 @@ __global__ void self_scatter_kernel(int n_reg, int GP, int g_begin, int g_count,
 }
 
 // flux = tally/(xstr*vol) + qbar*4pi   (kernel:165-173)
-__global__ void finalize_flux_kernel(int n_reg, int GP, int g_begin, int g_count, const double *__restrict__ tally,
+static __global__ void finalize_flux_kernel(int n_reg, int GP, int g_begin, int g_count, const double *__restrict__ tally,
                                      const double *__restrict__ xstr, const double *__restrict__ vol,
                                      const double *__restrict__ qbar, double *__restrict__ flux,
                                      const int32_t *__restrict__ reg_mask_begin, int reg_lo, int reg_hi)
@@ -318,7 +318,7 @@ __global__ void finalize_flux_kernel(int n_reg, int GP, int g_begin, int g_count
 }
 
 // host column layout [g_count][n] <-> device layout [n][GP]
-__global__ void scatter_columns_kernel(int64_t n, int GP, int g_begin, int g_count, const double *__restrict__ cols,
+static __global__ void scatter_columns_kernel(int64_t n, int GP, int g_begin, int g_count, const double *__restrict__ cols,
                                        double *__restrict__ dst)
 {
     const int64_t tot = n * g_count;
@@ -327,7 +327,7 @@ __global__ void scatter_columns_kernel(int64_t n, int GP, int g_begin, int g_cou
         dst[r * GP + g_begin + gl] = cols[i];
     }
 }
-__global__ void gather_columns_kernel(int64_t n, int GP, int g_begin, int g_count, const double *__restrict__ src,
+static __global__ void gather_columns_kernel(int64_t n, int GP, int g_begin, int g_count, const double *__restrict__ src,
                                       double *__restrict__ cols)
 {
     const int64_t tot = n * g_count;
@@ -337,7 +337,7 @@ __global__ void gather_columns_kernel(int64_t n, int GP, int g_begin, int g_coun
     }
 }
 
-__global__ void zero_groups_kernel(int64_t n, int GP, int g_begin, int g_count, double *__restrict__ dst)
+static __global__ void zero_groups_kernel(int64_t n, int GP, int g_begin, int g_count, double *__restrict__ dst)
 {
     const int64_t tot = n * g_count;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {

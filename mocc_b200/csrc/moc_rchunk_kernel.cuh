@@ -1,0 +1,707 @@
+// moc_rchunk_kernel.cuh -- per-group production sweep kernel, second generation (sm_100a):
+// REGISTER-RESIDENT CHUNKS IN STATICALLY PACKED BATCHES.
+//
+// Restates the same reference loops as moc_chunk_kernel.cuh
+//   sweep1g<CurrentWorker>              src/sweepers/moc/moc_sweeper_kernel.inc.hpp:84-133
+//   moc::Current::post_ray              src/sweepers/moc/moc_current_worker.hpp:202-264
+//   cmdo::CurrentCorrections::post_ray  src/sweepers/cmdo/correction_worker.hpp:109-205
+//   BoundaryCondition::update           src/core/boundary_condition.cpp:155-191
+// on the attenuation cache, one energy group per work item.
+//
+// What the first chunk kernel spent its time on (profiles/r1): 214 thread instructions and 77 shared-memory
+// wavefronts per segment position -- every (e, q) re-read from shared memory by compose and by both walks,
+// rolled loops with address arithmetic, one 5-step scan of three 64-bit values per polar angle for every
+// track however short, per-track descriptors / work counters / mailboxes. Here:
+//   * a track is cut into CHUNKS of exactly LMAX slots (the last one padded with neutral slots: attenuation
+//     1, q-bar 0, FSR id -1); chunks of many tracks are packed at set-up into BATCHES of NC chunks so that
+//     no track straddles a batch (first-fit decreasing; a track longer than a batch becomes a chained unit).
+//     Every batch is the same amount of work, whatever the track lengths: no lane idles on short tracks;
+//   * a TEAM of NW warps sweeps a batch: P lanes per chunk, one per polar angle of the bundle. A lane loads
+//     its chunk from shared memory ONCE (compose), keeps 1-e and q-bar in registers (fully unrolled, no address
+//     arithmetic) and walks it forward and backward from registers;
+//   * the flux entering every chunk comes from ONE scan over the lanes of the team. Track boundaries need no
+//     segmented scan: the first chunk of a track carries the map x -> 0 x + (A psi_in + B), which annihilates
+//     whatever precedes it (and likewise the last chunk for the backward direction);
+//   * staging as before -- attenuations and FSR ids by TMA bulk copies, q-bar gathered by 8-byte cp.async with
+//     the lanes on CONSECUTIVE slots, the tally reduced by one red.global.add.f64 per slot, again striped --
+//     but the next batch's attenuations and q-bar are requested as soon as compose has emptied the buffers
+//     (FSR ids triple-buffered), so they have the whole scan + walk + reduction to arrive.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "moc_chunk_kernel.cuh"
+
+namespace mocb200 {
+
+constexpr int kRcHead = 1; // first chunk of a track: the forward sweep starts here (incoming boundary flux)
+constexpr int kRcTail = 2; // last chunk of a track: the backward sweep starts here
+constexpr int kRcHeadCont = 4; // head of a later sub-block of a chained track: forward flux carried by the team
+constexpr int kRcTailCont = 8; // tail of an earlier sub-block: backward flux from the team's scratch
+
+// slots a team of NW warps sweeps at once, P lanes per chunk
+__host__ __device__ constexpr int rc_chunks(int P, int NW)
+{
+    return 32 * NW / P;
+}
+__host__ __device__ constexpr int rc_slots(int P, int LMAX, int NW)
+{
+    return rc_chunks(P, NW) * LMAX;
+}
+// dynamic shared memory of one team: attenuations [NS][P], q-bar [NS], contributions [NS][P] (doubles),
+// FSR ids [3][NS] (int32, triple-buffered); tally variants keep the crossing lists in global memory
+__host__ __device__ constexpr size_t rc_team_bytes(int P, int LMAX, int NW)
+{
+    return (size_t)rc_slots(P, LMAX, NW) * ((size_t)(2 * P + 1) * sizeof(double) + 3 * sizeof(int32_t));
+}
+
+struct RcArgs {
+    const int2 *units; // {first batch, batches}: swept by one team (batches > 1: one track longer than a batch)
+    int32_t n_units;
+    const int2 *pinfo; // per plane of the list: {macroplane, its first FSR}
+    int32_t n_planes;
+    const int2 *lane_meta; // per (chunk, polar angle): {flags | sweep angle << 8, index into bc_slots}
+    const int2 *bc_slots;  // per head / tail (chunk, polar angle): {incoming boundary slot, encoded outgoing slot}
+    const int2 *chunk_trk; // per chunk: {track (index into tracks), first position of the chunk in its track}
+    const ChunkUnit *tracks;
+    const int32_t *slot_fsr; // [n_slots] plane-local FSR id, -1: padding
+    const double *cache;     // attenuation cache of this list [plane][g][slot][P]
+    int64_t n_slots;
+    int32_t cache_groups, cache_g0;
+    const double *wt_v_st; // [n_plane][n_ang]
+    int32_t n_ang, bc_per_group;
+    int32_t g_begin, g_count, GP, n_reg;
+    const double *q; // group-major [g - g_begin][n_reg]
+    double *tally;   // same layout
+    const double *bc_in;
+    double *bc_out;
+    double *scratch; // per team: backward flux entering each sub-block of a chained track, [sub-block][P]
+    int32_t scratch_per_team;
+    // coarse-mesh tallies of the last inner (TALLY 1: moc::Current, 2: cmdo::CurrentCorrections)
+    const Cross *cross; // crossing lists with sentinels
+    const double *cur_w, *flx_w; // [n_plane][n_ang][2]
+    const int32_t *plane_surf_offset;
+    double *current, *surface_flux; // [n_surf][GP]
+    double *dsum, *ssum;
+    int32_t n_surf_plane, n_plane_total;
+};
+
+// launch geometry: slots per chunk, warps per team, teams per CTA
+struct RcConfig {
+    int LMAX, NW, TEAMS;
+};
+typedef void (*RcFn)(const RcArgs);
+// instantiated in moc_rc_p1.cu / moc_rc_p2.cu / moc_rc_p4.cu; nullptr: configuration not built
+RcFn pick_rc_kernel_p1(int tally, const RcConfig &c);
+RcFn pick_rc_kernel_p2(int tally, const RcConfig &c);
+RcFn pick_rc_kernel_p4(int tally, const RcConfig &c);
+
+template <int P, int LMAX, int NW, int TEAMS, int TALLY>
+__global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const RcArgs a)
+{
+    static_assert(P == 1 || P == 2 || P == 4, "one lane per polar angle: 1, 2 or 4 lanes per chunk");
+    static_assert(LMAX % 2 == 1, "odd chunk length: conflict-free shared-memory strides");
+    constexpr int T  = 32 * NW;             // lanes of a team
+    constexpr int NC = rc_chunks(P, NW);    // chunks per batch
+    constexpr int NS = rc_slots(P, LMAX, NW); // slots per batch
+    extern __shared__ __align__(16) double s_dyn[];
+    __shared__ uint64_t s_bar[4 * TEAMS];
+    __shared__ double s_tot[TEAMS][NW][P][4]; // per warp and polar angle: forward map (A, B), backward map (A, B) of the warp's chunks
+
+    const int lane = threadIdx.x & 31;
+    const int wid  = threadIdx.x >> 5;
+    const int team = wid / NW, wl = wid - team * NW;
+    const int tl   = wl * 32 + lane;     // lane within the team
+    const int c    = tl / P, p = tl % P; // chunk within the batch, polar angle of the bundle
+    const bool loader = tl == 0;
+    char *wbase   = reinterpret_cast<char *>(s_dyn) + (size_t)team * rc_team_bytes(P, LMAX, NW);
+    double *exb   = reinterpret_cast<double *>(wbase);
+    double *qb    = exb + (size_t)NS * P;
+    double *ab    = qb + NS;
+    int32_t *fbuf = reinterpret_cast<int32_t *>(ab + (size_t)NS * P); // three FSR-id buffers
+    uint64_t *bar = &s_bar[4 * team];                                 // [0..2] FSR-id buffers, [3] attenuations
+    auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(T) : "memory"); };
+    if (loader) {
+        for (int i = 0; i < 4; i++)
+            mbar_init(bar + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    team_sync();
+    uint32_t par_f = 0u, par_e = 0u; // mbarrier phase parities (bit i of par_f: FSR-id buffer i)
+
+    const int GP            = a.GP;
+    const uint32_t per_unit = (uint32_t)a.n_planes * (uint32_t)a.g_count;
+    const uint32_t total    = (uint32_t)a.n_units * per_unit;
+    const uint32_t n_teams  = gridDim.x * TEAMS;
+    const uint32_t team_global = blockIdx.x * TEAMS + team;
+
+    // work item -> (unit, plane of the list, group of the launch)
+    struct Item {
+        int batch, nb; // first batch, batches of the unit
+        int ipl, grel, plane, first_reg;
+    };
+    auto decode = [&](uint32_t w) {
+        Item it;
+        const uint32_t unit = w / per_unit;
+        const uint32_t r    = w - unit * per_unit;
+        it.ipl              = (int)(r / (uint32_t)a.g_count);
+        it.grel             = (int)(r - (uint32_t)it.ipl * (uint32_t)a.g_count);
+        const int2 u        = __ldg(a.units + unit);
+        it.batch = u.x, it.nb = u.y;
+        const int2 pi = __ldg(a.pinfo + it.ipl);
+        it.plane = pi.x, it.first_reg = pi.y;
+        return it;
+    };
+    auto ex_of = [&](const Item &it, int batch) {
+        const int g = a.g_begin + it.grel;
+        return a.cache + (((size_t)it.ipl * a.cache_groups + (g - a.cache_g0)) * a.n_slots + (size_t)batch * NS) * P;
+    };
+    // ---- staging ----
+    auto issue_fsr = [&](int fi, int batch) {
+        if (loader) {
+            constexpr uint32_t bytes = (uint32_t)NS * 4u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar + fi, bytes);
+            bulk_g2s(fbuf + fi * NS, a.slot_fsr + (size_t)batch * NS, bytes, bar + fi);
+        }
+    };
+    auto issue_ex = [&](const Item &it, int batch) {
+        if (loader) {
+            constexpr uint32_t bytes = (uint32_t)NS * (uint32_t)P * 8u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar + 3, bytes);
+            const char *src = reinterpret_cast<const char *>(ex_of(it, batch));
+            for (uint32_t off = 0; off < bytes; off += 16384u)
+                bulk_g2s(reinterpret_cast<char *>(exb) + off, src + off, min(16384u, bytes - off), bar + 3);
+        }
+    };
+    auto gather_q = [&](int fi, const Item &it) { // striped: lanes on consecutive slots
+        mbar_wait(bar + fi, (par_f >> fi) & 1u);
+        par_f ^= 1u << fi;
+        const double *qf  = a.q + (size_t)it.grel * a.n_reg + it.first_reg;
+        const int32_t *fb = fbuf + fi * NS;
+#pragma unroll
+        for (int j = 0; j < (NS + T - 1) / T; j++) {
+            const int i = tl + j * T;
+            if (NS % T == 0 || i < NS) {
+                const int f = fb[i];
+                if (f >= 0)
+                    cp_async_8(qb + i, qf + f);
+                else
+                    qb[i] = 0.0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto wait_staged = [&]() {
+        mbar_wait(bar + 3, par_e);
+        par_e ^= 1u;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        team_sync();
+    };
+    auto reduce_tally = [&](int fi, const Item &it) { // striped again: one red per slot
+        double *tf        = a.tally + (size_t)it.grel * a.n_reg + it.first_reg;
+        const int32_t *fb = fbuf + fi * NS;
+#pragma unroll
+        for (int j = 0; j < (NS + T - 1) / T; j++) {
+            const int i = tl + j * T;
+            if (NS % T == 0 || i < NS) {
+                const int f = fb[i];
+                double v;
+                if constexpr (P == 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(ab + 2 * i);
+                    v = t.x + t.y;
+                } else if constexpr (P == 4) {
+                    const double2 t = *reinterpret_cast<const double2 *>(ab + 4 * i);
+                    const double2 u = *reinterpret_cast<const double2 *>(ab + 4 * i + 2);
+                    v = (t.x + t.y) + (u.x + u.y);
+                } else {
+                    v = ab[i];
+                }
+                if (f >= 0)
+                    atomicAdd(tf + f, v);
+            }
+        }
+    };
+
+    // ---- the lane's chunk: load once, keep 1 - e and q-bar in registers ----
+    struct Maps {
+        double Af, Bf, Ab, Bb;
+    };
+    auto compose = [&](double (&ome)[LMAX], double (&qv)[LMAX]) {
+        const double *el = exb + (size_t)c * LMAX * P + p;
+        const double *ql = qb + c * LMAX;
+        double A = 1.0, Bf = 0.0, Bb = 0.0;
+#pragma unroll
+        for (int k = 0; k < LMAX; k++) {
+            const double e = el[k * P];
+            qv[k]  = ql[k];
+            ome[k] = 1.0 - e;
+            const double bq = qv[k] * ome[k];
+            Bb = fma(A, bq, Bb); // M o m_k: the backward sweep applies the higher slot first
+            Bf = fma(e, Bf, bq); // m_k o M
+            A *= e;
+        }
+        return Maps{A, Bf, A, Bb};
+    };
+    // Scan over the chunks of the team. In: the forward / backward map of the lane's chunk (with the resets of
+    // track heads / tails folded in). Out: the flux entering the chunk in both directions (valid for chunks that
+    // are not heads / tails themselves); tf/tb: the team's total maps (chained tracks).
+    auto scan = [&](const Maps &m, double &psi_f, double &psi_b, Maps *team_total) {
+        double EfA = 1.0, EfB = 0.0, EbA = 1.0, EbB = 0.0;
+        double TAf = m.Af, TF = m.Bf, TAb = m.Ab, TB = m.Bb;
+#pragma unroll
+        for (int s = P; s < 32; s <<= 1) {
+            const bool upper = (lane & s) != 0; // the partner block holds the LOWER chunks
+            const double oAf = __shfl_xor_sync(0xffffffffu, TAf, s);
+            const double oF  = __shfl_xor_sync(0xffffffffu, TF, s);
+            const double oAb = __shfl_xor_sync(0xffffffffu, TAb, s);
+            const double oB  = __shfl_xor_sync(0xffffffffu, TB, s);
+            if (upper) {
+                EfB = fma(EfA, oF, EfB); // forward: the lower block first, then what I already have below me
+                EfA *= oAf;
+                TF = fma(TAf, oF, TF);   // merged block, forward: lower (partner) then upper (mine)
+                TB = fma(oAb, TB, oB);   // backward: upper (mine) then lower (partner)
+            } else {
+                EbB = fma(EbA, oB, EbB); // backward: the upper block first, then what I already have above me
+                EbA *= oAb;
+                TF = fma(oAf, TF, oF);
+                TB = fma(TAb, oB, TB);
+            }
+            TAf *= oAf;
+            TAb *= oAb;
+        }
+        double cf = 0.0, cb = 0.0; // flux leaving the lower / higher warps (the first chunk of a batch is a head)
+        if (NW > 1) {
+            if (lane < P) { // every lane of polar angle p holds the warp's total maps
+                s_tot[team][wl][p][0] = TAf, s_tot[team][wl][p][1] = TF;
+                s_tot[team][wl][p][2] = TAb, s_tot[team][wl][p][3] = TB;
+            }
+            team_sync();
+#pragma unroll
+            for (int w = 0; w < NW - 1; w++)
+                if (w < wl)
+                    cf = fma(s_tot[team][w][p][0], cf, s_tot[team][w][p][1]);
+#pragma unroll
+            for (int w = NW - 1; w > 0; w--)
+                if (w > wl)
+                    cb = fma(s_tot[team][w][p][2], cb, s_tot[team][w][p][3]);
+            if (team_total) { // maps of the whole team (valid in every lane)
+                double af = 1.0, bf = 0.0, ab_ = 1.0, bb = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    bf = fma(s_tot[team][w][p][0], bf, s_tot[team][w][p][1]);
+                    af *= s_tot[team][w][p][0];
+                }
+#pragma unroll
+                for (int w = NW - 1; w >= 0; w--) {
+                    bb = fma(s_tot[team][w][p][2], bb, s_tot[team][w][p][3]);
+                    ab_ *= s_tot[team][w][p][2];
+                }
+                *team_total = Maps{af, bf, ab_, bb};
+            }
+        } else if (team_total) {
+            *team_total = Maps{TAf, TF, TAb, TB};
+        }
+        psi_f = fma(EfA, cf, EfB);
+        psi_b = fma(EbA, cb, EbB);
+    };
+    // both walks from registers (kernel:103-129); contributions of the lane's polar angle to ab[slot][p]
+    auto walk = [&](const double (&ome)[LMAX], const double (&qv)[LMAX], double wt, double &psi_f, double &psi_b) {
+        double s[LMAX];
+#pragma unroll
+        for (int k = 0; k < LMAX; k++) {
+            const double d = (psi_f - qv[k]) * ome[k];
+            psi_f -= d;
+            s[k] = d * wt;
+        }
+        double *al = ab + (size_t)c * LMAX * P + p;
+#pragma unroll
+        for (int k = LMAX - 1; k >= 0; k--) {
+            const double d = (psi_b - qv[k]) * ome[k];
+            psi_b -= d;
+            al[k * P] = fma(d, wt, s[k]);
+        }
+    };
+    // The walks of the last inner: as `walk`, plus moc::Current::post_ray (moc_current_worker.hpp:202-264) or
+    // cmdo::CurrentCorrections::post_ray (correction_worker.hpp:109-205) at the coarse-surface crossings inside
+    // the lane's chunk, for the lane's own polar angle (sweep angle `ang`).
+    auto walk_tally = [&](const double (&ome)[LMAX], const double (&qv)[LMAX], double wt, double &psi_f, double &psi_b,
+                          const Item &it, int batch, int fi_cur, int ang) {
+        const int2 ct = __ldg(a.chunk_trk + (size_t)batch * NC + c);
+        const int k0  = ct.y;
+        int nseg = 0, n_fw = 0, n_bw = 0;
+        const Cross *xfl = a.cross, *xbl = a.cross;
+        if (ct.x >= 0) {
+            const ChunkUnit &u = a.tracks[ct.x];
+            nseg = u.nseg, n_fw = u.n_fw, n_bw = u.n_bw;
+            xfl = a.cross + u.cross_begin, xbl = xfl + n_fw + 1;
+        }
+        const size_t wo  = ((size_t)it.plane * a.n_ang + ang) * 2;
+        const double cw0 = a.cur_w[wo], cw1 = a.cur_w[wo + 1], fw0 = a.flx_w[wo], fw1 = a.flx_w[wo + 1];
+        const int surf_off = a.plane_surf_offset[it.plane];
+        const int g        = a.g_begin + it.grel;
+        const int nslot    = 2 * a.n_ang;
+        const int32_t *fb  = fbuf + fi_cur * NS + c * LMAX;
+        auto tally_cross = [&](const Cross &x, double psi, int dir) {
+            const int norm = x.surf & 1;
+            const int surf = x.surf >> 1;
+            const size_t o = (size_t)(surf + surf_off) * GP + g;
+            const double cs = psi * (norm ? cw1 : cw0), fs = psi * (norm ? fw1 : fw0);
+            // forward adds, backward subtracts (moc_current_worker.hpp:230-231); the corrections worker also
+            // subtracts the backward SURFACE FLUX (correction_worker.hpp:136-137, 194-195)
+            atomicAdd(&a.current[o], dir ? -cs : cs);
+            atomicAdd(&a.surface_flux[o], (dir && TALLY == 2) ? -fs : fs);
+            if (TALLY == 2) {
+                const size_t so = (size_t)it.grel * a.n_plane_total * a.n_ang * a.n_surf_plane * 2 +
+                                  (((size_t)it.plane * a.n_ang + ang) * a.n_surf_plane + surf) * 2 + dir;
+                atomicAdd(&a.ssum[so], psi);
+            }
+        };
+        auto dsum_add = [&](int f, int dir, double d) {
+            const size_t o = (size_t)it.grel * a.n_reg * nslot + (size_t)(f + it.first_reg) * nslot + ang * 2 + dir;
+            atomicAdd(&a.dsum[o], d);
+        };
+        auto lower_bound = [](const Cross *l, int n, int node) {
+            int a0 = 0, a1 = n; // first index with l[i].node >= node (the sentinel at n has node INT32_MAX)
+            while (a0 < a1) {
+                const int m = (a0 + a1) >> 1;
+                if (l[m].node < node)
+                    a0 = m + 1;
+                else
+                    a1 = m;
+            }
+            return a0;
+        };
+        const int kt_end = min(k0 + LMAX, nseg); // track positions [k0, kt_end) are real
+        const bool any   = kt_end > k0;
+        int ci_f = 0, ci_b = 0;
+        Cross xf{INT32_MAX, 0}, xb{INT32_MAX, 0};
+        if (any) {
+            ci_f = lower_bound(xfl, n_fw, k0);
+            ci_b = lower_bound(xbl, n_bw, nseg - kt_end);
+            xf = xfl[ci_f], xb = xbl[ci_b];
+        }
+        double s[LMAX];
+#pragma unroll
+        for (int k = 0; k < LMAX; k++) {
+            const int kt     = k0 + k; // the forward flux at the node in front of position kt
+            const bool valid = kt < kt_end;
+            if (valid) {
+                while (xf.node == kt) {
+                    tally_cross(xf, psi_f, 0);
+                    xf = xfl[++ci_f];
+                }
+            }
+            const double d = (psi_f - qv[k]) * ome[k];
+            psi_f -= d;
+            s[k] = d * wt;
+            if (valid) {
+                if (TALLY == 2)
+                    dsum_add(fb[k], 0, d);
+                if (kt == nseg - 1) { // far end of the ray
+                    while (xf.node == nseg) {
+                        tally_cross(xf, psi_f, 0);
+                        xf = xfl[++ci_f];
+                    }
+                }
+            }
+        }
+        double *al = ab + (size_t)c * LMAX * P + p;
+#pragma unroll
+        for (int k = LMAX - 1; k >= 0; k--) {
+            const int kt     = k0 + k;
+            const bool valid = kt < kt_end;
+            if (valid) {
+                const int nbw = nseg - 1 - kt; // segments walked by the backward sweep so far
+                while (xb.node == nbw) {
+                    tally_cross(xb, psi_b, 1);
+                    xb = xbl[++ci_b];
+                }
+            }
+            const double d = (psi_b - qv[k]) * ome[k];
+            psi_b -= d;
+            al[k * P] = fma(d, wt, s[k]);
+            if (valid) {
+                if (TALLY == 2)
+                    dsum_add(fb[k], 1, d);
+                if (kt == 0) { // near end of the ray
+                    while (xb.node == nseg) {
+                        tally_cross(xb, psi_b, 1);
+                        xb = xbl[++ci_b];
+                    }
+                }
+            }
+        }
+    };
+    auto store_exit = [&](const Item &it, int enc, double v) {
+        if (enc != INT32_MIN) {
+            double *bc_out_pl = a.bc_out + (size_t)it.plane * a.bc_per_group * GP + (a.g_begin + it.grel);
+            bc_out_pl[(size_t)(enc >= 0 ? enc : -(enc + 1)) * GP] = enc >= 0 ? v : 0.0;
+        }
+    };
+    auto load_in = [&](const Item &it, int slot) {
+        return a.bc_in[((size_t)it.plane * a.bc_per_group + slot) * GP + (a.g_begin + it.grel)];
+    };
+
+    // ================= pipeline over the work items of this team (static round-robin) =================
+    // Invariant at the top of a single-batch item `cur` with `staged`: its FSR ids are in buffer fi, its attenuations
+    // and q-bar are on their way, its lane descriptors are in registers; if the next item is a single batch too,
+    // its FSR ids have been requested into buffer (fi + 1) % 3.
+    uint32_t w_cur = team_global;
+    if (w_cur >= total)
+        return;
+    Item cur = decode(w_cur);
+    uint32_t w_nxt = w_cur + n_teams;
+    Item nxt{};
+    if (w_nxt < total)
+        nxt = decode(w_nxt);
+    int fi = 0; // FSR-id buffer of `cur`
+    int2 meta = make_int2(0, 0), bcs = make_int2(0, INT32_MIN);
+    bool staged = false;
+    double *sc  = a.scratch + (size_t)team_global * a.scratch_per_team;
+
+    while (true) {
+        const bool have_nxt = w_nxt < total;
+        if (!staged && cur.nb == 1) { // (re)start the pipeline at `cur`
+            meta = __ldg(a.lane_meta + (size_t)cur.batch * NC * P + tl);
+            bcs  = (meta.x & (kRcHead | kRcTail)) ? __ldg(a.bc_slots + meta.y) : make_int2(0, INT32_MIN);
+            issue_fsr(fi, cur.batch);
+            issue_ex(cur, cur.batch);
+            if (have_nxt && nxt.nb == 1)
+                issue_fsr((fi + 1) % 3, nxt.batch);
+            gather_q(fi, cur);
+            staged = true;
+        }
+        if (cur.nb == 1) {
+            // ---------------- one batch: the common case ----------------
+            const int flags = meta.x & 0xff;
+            const bool head = flags & kRcHead, tail = flags & kRcTail;
+            const double wt = __ldg(a.wt_v_st + cur.plane * a.n_ang + (meta.x >> 8));
+            double pin = 0.0;
+            if (head || tail)
+                pin = load_in(cur, bcs.x);
+            const int out_enc = bcs.y;
+            wait_staged();
+            double ome[LMAX], qv[LMAX];
+            Maps m = compose(ome, qv);
+            team_sync(); // attenuation and q-bar buffers are free; everybody has left the previous reduction
+            // the next item: attenuations, q-bar (its FSR ids were requested one item earlier), lane descriptors;
+            // the item after it: FSR ids
+            const bool pre = have_nxt && nxt.nb == 1;
+            const uint32_t w_nn = w_nxt + n_teams;
+            Item nn{};
+            if (have_nxt && w_nn < total)
+                nn = decode(w_nn);
+            int2 meta_n = make_int2(0, 0);
+            if (pre) {
+                issue_ex(nxt, nxt.batch);
+                if (w_nn < total && nn.nb == 1)
+                    issue_fsr((fi + 2) % 3, nn.batch);
+                gather_q((fi + 1) % 3, nxt);
+                meta_n = __ldg(a.lane_meta + (size_t)nxt.batch * NC * P + tl);
+            }
+            if (head)
+                m.Bf = fma(m.Af, pin, m.Bf), m.Af = 0.0;
+            if (tail)
+                m.Bb = fma(m.Ab, pin, m.Bb), m.Ab = 0.0;
+            double psi_f, psi_b;
+            scan(m, psi_f, psi_b, nullptr);
+            if (head)
+                psi_f = pin;
+            if (tail)
+                psi_b = pin;
+            int2 bcs_n = make_int2(0, INT32_MIN);
+            if (pre && (meta_n.x & (kRcHead | kRcTail)))
+                bcs_n = __ldg(a.bc_slots + meta_n.y);
+            if constexpr (TALLY == 0)
+                walk(ome, qv, wt, psi_f, psi_b);
+            else
+                walk_tally(ome, qv, wt, psi_f, psi_b, cur, cur.batch, fi, meta.x >> 8);
+            if (tail)
+                store_exit(cur, out_enc, psi_f);
+            if (head)
+                store_exit(cur, out_enc, psi_b);
+            team_sync(); // contributions complete
+            reduce_tally(fi, cur);
+            if (!have_nxt)
+                break;
+            if (pre) {
+                fi = (fi + 1) % 3;
+                meta = meta_n, bcs = bcs_n;
+            } else {
+                staged = false;
+                team_sync(); // the chained unit that follows reuses the buffers at once
+            }
+            w_cur = w_nxt, cur = nxt, w_nxt = w_nn, nxt = nn;
+        } else {
+            // ---------------- a track longer than a batch: sub-blocks chained by a carried flux ----------------
+            // Not pipelined. Sub-block b holds chunks [b NC, (b + 1) NC) of the track; its first chunk is the head
+            // of the track (b == 0) or continues the forward sweep with the flux the team carries, its last chunk is
+            // the tail of the track (b == nb - 1) or continues the backward sweep with the flux pass A left in `sc`.
+            const int nb = cur.nb;
+            auto stage_block = [&](int b, int2 &mt, int2 &bs) {
+                mt = __ldg(a.lane_meta + (size_t)(cur.batch + b) * NC * P + tl);
+                bs = (mt.x & (kRcHead | kRcTail)) ? __ldg(a.bc_slots + mt.y) : make_int2(0, INT32_MIN);
+                issue_fsr(fi, cur.batch + b);
+                issue_ex(cur, cur.batch + b);
+                gather_q(fi, cur);
+                wait_staged();
+            };
+            // pass A, highest sub-block first: the backward flux entering sub-block b - 1 from above
+            for (int b = nb - 1; b >= 1; --b) {
+                int2 mt, bs;
+                stage_block(b, mt, bs);
+                double ome[LMAX], qv[LMAX];
+                Maps m = compose(ome, qv);
+                const int flags = mt.x & 0xff;
+                if (flags & kRcTail) // the tail of the track: incoming boundary flux
+                    m.Bb = fma(m.Ab, load_in(cur, bs.x), m.Bb), m.Ab = 0.0;
+                if (flags & kRcTailCont) // written by this loop's previous trip
+                    m.Bb = fma(m.Ab, sc[b * P + p], m.Bb), m.Ab = 0.0;
+                double pf, pb;
+                Maps tot;
+                scan(m, pf, pb, &tot);
+                if (tl < P) // the total backward map has A = 0 (a tail was folded in): B is the flux leaving below
+                    sc[(b - 1) * P + p] = tot.Bb;
+                team_sync();
+            }
+            // pass B, lowest sub-block first: forward chain, both walks, tally
+            double cfk = 0.0;
+            for (int b = 0; b < nb; ++b) {
+                int2 mt, bs;
+                stage_block(b, mt, bs);
+                const int flags = mt.x & 0xff;
+                const double wt = __ldg(a.wt_v_st + cur.plane * a.n_ang + (mt.x >> 8));
+                double ome[LMAX], qv[LMAX];
+                Maps m = compose(ome, qv);
+                const bool head = flags & kRcHead, tail = flags & kRcTail;
+                const bool start_f = flags & (kRcHead | kRcHeadCont), start_b = flags & (kRcTail | kRcTailCont);
+                double pin_f = 0.0, pin_b = 0.0;
+                if (start_f)
+                    pin_f = head ? load_in(cur, bs.x) : cfk;
+                if (start_b)
+                    pin_b = tail ? load_in(cur, bs.x) : sc[b * P + p];
+                if (start_f)
+                    m.Bf = fma(m.Af, pin_f, m.Bf), m.Af = 0.0;
+                if (start_b)
+                    m.Bb = fma(m.Ab, pin_b, m.Bb), m.Ab = 0.0;
+                double psi_f, psi_b;
+                Maps tot;
+                scan(m, psi_f, psi_b, &tot);
+                if (start_f)
+                    psi_f = pin_f;
+                if (start_b)
+                    psi_b = pin_b;
+                if constexpr (TALLY == 0)
+                    walk(ome, qv, wt, psi_f, psi_b);
+                else
+                    walk_tally(ome, qv, wt, psi_f, psi_b, cur, cur.batch + b, fi, mt.x >> 8);
+                if (tail)
+                    store_exit(cur, bs.y, psi_f);
+                if (head)
+                    store_exit(cur, bs.y, psi_b);
+                cfk = tot.Bf; // forward flux leaving the sub-block (total A = 0: a head was folded in)
+                team_sync();
+                reduce_tally(fi, cur);
+                team_sync();
+            }
+            if (!have_nxt)
+                break;
+            w_cur = w_nxt, cur = nxt;
+            w_nxt = w_cur + n_teams;
+            if (w_nxt < total)
+                nxt = decode(w_nxt);
+            staged = false;
+        }
+    }
+}
+
+
+// Fills the attenuation cache of a packed list for groups [g_begin, g_begin + g_count): the same table
+// lookup of -xstr*len/sin(theta) as exp_cache_kernel (exponential.hpp:69-79), one thread per slot; padding
+// slots get the identity (1.0). Layout [plane][g][slot][P].
+struct RcCacheArgs {
+    const int2 *chunk_trk;
+    const ChunkUnit *tracks;
+    const int4 *len_begin; // per track and polar angle: start of that angle's own (padded) segment lengths
+    const int32_t *planes;
+    int32_t n_planes, lmax;
+    int64_t n_slots;
+    const double *seg_len;
+    const int32_t *seg_fsr;
+    const double *ang_rsintheta;
+    const int32_t *plane_first_reg;
+    const double *xstr; // [n_reg][GP]
+    int32_t g_begin, g_count, cache_groups, cache_g0, GP;
+    double *cache;
+    const double *exp_table;
+    int32_t exp_n;
+    double exp_min, exp_max;
+};
+
+template <int P> __global__ void __launch_bounds__(512, 1) rc_cache_kernel(const RcCacheArgs a)
+{
+    extern __shared__ __align__(16) double s_tab[];
+    for (int i = threadIdx.x; i < a.exp_n + 2; i += blockDim.x)
+        s_tab[i] = a.exp_table[i];
+    __syncthreads();
+    const double space  = (a.exp_max - a.exp_min) / (double)a.exp_n;
+    const double rspace = 1.0 / space;
+    const double c0     = -a.exp_min * rspace;
+    const int64_t total = a.n_slots * a.n_planes;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ipl     = (int)(i / a.n_slots);
+        const int64_t s   = i - (int64_t)ipl * a.n_slots;
+        const int chunk   = (int)(s / a.lmax);
+        const int k       = (int)(s - (int64_t)chunk * a.lmax);
+        const int2 ct     = a.chunk_trk[chunk];
+        bool valid        = ct.x >= 0;
+        int reg           = 0;
+        double len[P], nrs[P];
+#pragma unroll
+        for (int p = 0; p < P; p++)
+            len[p] = 0.0, nrs[p] = 0.0;
+        if (valid) {
+            const ChunkUnit &u = a.tracks[ct.x];
+            valid              = ct.y + k < u.nseg;
+            if (valid) {
+                const int plane = a.planes[ipl];
+                reg             = a.seg_fsr[u.seg_begin + ct.y + k] + a.plane_first_reg[plane];
+                const int4 lb4  = a.len_begin[ct.x];
+                const int lb[4] = {lb4.x, lb4.y, lb4.z, lb4.w};
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    len[p] = a.seg_len[lb[p] + ct.y + k];
+                    nrs[p] = -a.ang_rsintheta[u.ang[p]];
+                }
+            }
+        }
+        for (int gi = 0; gi < a.g_count; gi++) {
+            const int g = a.g_begin + gi;
+            double ex[P];
+            if (valid) {
+                const double xs = a.xstr[(size_t)reg * a.GP + g];
+#pragma unroll
+                for (int p = 0; p < P; p++)
+                    ex[p] = exp_interp(s_tab, xs * len[p] * nrs[p], c0, rspace);
+            } else {
+#pragma unroll
+                for (int p = 0; p < P; p++)
+                    ex[p] = 1.0;
+            }
+            double *dst = a.cache + (((size_t)ipl * a.cache_groups + (g - a.cache_g0)) * a.n_slots + s) * P;
+            if constexpr (P == 2) {
+                *reinterpret_cast<double2 *>(dst) = make_double2(ex[0], ex[1]);
+            } else if constexpr (P == 4) {
+                *reinterpret_cast<double2 *>(dst)     = make_double2(ex[0], ex[1]);
+                *reinterpret_cast<double2 *>(dst + 2) = make_double2(ex[2], ex[3]);
+            } else {
+                dst[0] = ex[0];
+            }
+        }
+    }
+}
+
+} // namespace mocb200

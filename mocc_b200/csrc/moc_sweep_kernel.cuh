@@ -174,7 +174,7 @@ __device__ __forceinline__ int tpos(int s)
 }
 
 template <int GL, int P, int TALLY, bool CACHED>
-__global__ void __launch_bounds__(kWarpBlock, 1) sweep_warp_kernel(const WarpArgs a)
+static __global__ void __launch_bounds__(kWarpBlock, 1) sweep_warp_kernel(const WarpArgs a)
 {
     constexpr int C       = 4;
     constexpr int NCH     = 32 / GL; // chunk lanes per warp
@@ -738,7 +738,7 @@ template <int P> __global__ void __launch_bounds__(512, 1) exp_cache_kernel(cons
 // q-bar = (src + flux*xs_self) * (1/(xstr_src*4pi)) (source_isotropic.cpp:29-31, non-contracted
 // arithmetic) into every layout the sweep kernels read, plus the tally reset.
 //   group_major: q_out/tally_out are [g - g_begin][n_reg], else [n_reg][GP]; xq gets {xstr, q}.
-__global__ void self_scatter_q_kernel(int n_reg, int GP, int g_begin, int g_count, const double *__restrict__ src,
+static __global__ void self_scatter_q_kernel(int n_reg, int GP, int g_begin, int g_count, const double *__restrict__ src,
                                       const double *__restrict__ flux, const double *__restrict__ xs_self,
                                       const double *__restrict__ xstr_src, const double *__restrict__ xstr,
                                       double *qbar, double *q_out, double2 *__restrict__ xq,
@@ -777,7 +777,7 @@ __global__ void self_scatter_q_kernel(int n_reg, int GP, int g_begin, int g_coun
 }
 
 // flux = tally/(xstr*vol) + qbar*4pi   (kernel:165-173), tally in either layout
-__global__ void finalize_flux_q_kernel(int n_reg, int GP, int g_begin, int g_count, const double *__restrict__ tally,
+static __global__ void finalize_flux_q_kernel(int n_reg, int GP, int g_begin, int g_count, const double *__restrict__ tally,
                                        const double *__restrict__ xstr, const double *__restrict__ vol,
                                        const double *__restrict__ qbar, double *__restrict__ flux, int reg_lo,
                                        int reg_hi, int group_major)
@@ -803,7 +803,7 @@ __global__ void finalize_flux_q_kernel(int n_reg, int GP, int g_begin, int g_cou
 // finalize_flux_q_kernel of inner iteration i fused with self_scatter_q_kernel of iteration i + 1 (group-major
 // q-bar / tally of the per-group sweeps): flux = tally/(xstr*vol) + qbar*4pi; qbar' = (src + flux*xs_self) /
 // (xstr_src*4pi); tally = 0; work counters = 0. Same non-contracted arithmetic as the two kernels.
-__global__ void finalize_next_q_kernel(int n_reg, int GP, int g_begin, int g_count, double *__restrict__ tally,
+static __global__ void finalize_next_q_kernel(int n_reg, int GP, int g_begin, int g_count, double *__restrict__ tally,
                                        const double *__restrict__ xstr, const double *__restrict__ vol,
                                        double *__restrict__ qbar, double *__restrict__ flux, int reg_lo, int reg_hi,
                                        const double *__restrict__ src, const double *__restrict__ xs_self,
@@ -856,7 +856,7 @@ struct CorrArgs {
     double *beta;  // [g][2 n_ang][n_cell_total]
 };
 
-__global__ void corrections_kernel(const CorrArgs a)
+static __global__ void corrections_kernel(const CorrArgs a)
 {
     const int64_t per_g = (int64_t)a.n_planes * a.n_ang * a.n_cell_plane * 2;
     const int64_t total = per_g * a.g_count;

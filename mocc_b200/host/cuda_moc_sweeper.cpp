@@ -54,6 +54,8 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
         opt.kernel = MOCB200_KERNEL_ITEM;
     else if (kernel == "chunk")
         opt.kernel = MOCB200_KERNEL_CHUNK;
+    else if (kernel == "rchunk")
+        opt.kernel = MOCB200_KERNEL_RCHUNK;
     else
         throw EXCEPT("Unrecognized <cuda kernel=...> option.");
     if (allow_splitting_ && group_batch_)

@@ -55,7 +55,7 @@ def _check(res, ref, k_tol, flux_tol, same_outers=True):
 
 @pytest.mark.parametrize("xml,gold", [("mini2d.xml", "mini2d_solve_ref.arrays.gz"),
                                       ("3x3.xml", "3x3_solve_ref.arrays.gz")])
-@pytest.mark.parametrize("kernel", ["chunk", "cached", "track", "item"])
+@pytest.mark.parametrize("kernel", ["rchunk", "chunk", "cached", "track", "item"])
 def test_eigenvalue_solve_matches_reference(tmp_path, xml, gold, kernel):
     res = _solve(tmp_path, xml, ["solver/sweeper@type=moc_cuda", f"solver/sweeper/cuda@kernel={kernel}"])
     _check(res, _golden(gold), k_tol=1e-9, flux_tol=1e-8)

@@ -64,7 +64,7 @@ def _xy_mask(flat):
 
 @pytest.mark.parametrize("case", [c for c in sorted(CASES) if c != "mini3d_2d3d"])
 @pytest.mark.parametrize("max_polar", [1, 2, 4])
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
 def test_sweep1g_matches_reference_golden(case, max_polar, kernel):
     flat, gold = load_case(case)
     gs = bool(gold["gs_boundary"][0])
@@ -90,6 +90,27 @@ def test_chunk_kernel_superblocks_match_reference_golden(case, max_polar, chunk_
     flat, gold = load_case(case)
     gs = bool(gold["gs_boundary"][0])
     sw = _sweeper(flat, boundary_update=0 if gs else 1, max_polar=max_polar, kernel=4, chunk_cap=chunk_cap)
+    xy = _xy_mask(flat)
+    for rec in records(gold):
+        flux, bc_out, cur, sf = _run_record(sw, flat, rec)
+        _close(flux, rec["flux_out"])
+        _close(bc_out, rec["bc_out"])
+        if cur is not None:
+            area = flat["surf_area"]
+            _close(cur[xy] / area[xy], rec["current"][xy], atol=1e-13)
+            _close(sf[xy] / area[xy], rec["surface_flux"][xy], atol=1e-13)
+    sw.close()
+
+
+@pytest.mark.parametrize("case", ["mini2d_gs", "mini2d_jacobi", "mini3d_gs", "3x3_s05_gs"])
+@pytest.mark.parametrize("max_polar", [1, 2, 4])
+@pytest.mark.parametrize("chunk_cap", [14, 40, 100])
+def test_rchunk_kernel_chained_units_match_reference_golden(case, max_polar, chunk_cap):
+    """RCHUNK kernel with few chunks per batch: every longer track becomes a chained unit (sub-blocks linked by a
+    carried flux, two passes), single-batch and chained units interleaved in the work list."""
+    flat, gold = load_case(case)
+    gs = bool(gold["gs_boundary"][0])
+    sw = _sweeper(flat, boundary_update=0 if gs else 1, max_polar=max_polar, kernel=5, chunk_cap=chunk_cap)
     xy = _xy_mask(flat)
     for rec in records(gold):
         flux, bc_out, cur, sf = _run_record(sw, flat, rec)
@@ -187,7 +208,7 @@ def test_batched_groups_match_oracle(case, jacobi, kernel):
     sw.close()
 
 
-@pytest.mark.parametrize("kernel", [2, 3, 4, -4])
+@pytest.mark.parametrize("kernel", [2, 3, 4, -4, 5, -5])
 @pytest.mark.parametrize("max_polar", [1, 2])
 def test_corrections_match_reference_golden(kernel, max_polar):
     """MOCB200_TALLY_CORRECTIONS == the reference's MoCSweeper_2D3D last inner (cmdo::CurrentCorrections):
@@ -197,7 +218,8 @@ def test_corrections_match_reference_golden(kernel, max_polar):
     recs = [r for r in records(gold) if int(r["mode"][0]) == 2]
     assert recs
     # kernel -4: the chunk kernel with a 64-segment staging cap and two-warp teams (super-block chaining)
-    kw = dict(kernel=4, chunk_cap=-64) if kernel == -4 else dict(kernel=kernel)
+    # kernel -5: the register-chunk kernel with three chunks per batch (chained units)
+    kw = dict(kernel=4, chunk_cap=-64) if kernel == -4 else (dict(kernel=5, chunk_cap=40) if kernel == -5 else dict(kernel=kernel))
     sw = _sweeper(flat, boundary_update=0, max_polar=max_polar, **kw)
     xy = _xy_mask(flat)
     area = flat["surf_area"]
@@ -313,7 +335,7 @@ def c5g7_2d_flat():
     return load_arrays(bench.workload_files())
 
 
-@pytest.mark.parametrize("kernel,jacobi", [(0, False), (0, True), (3, False)])
+@pytest.mark.parametrize("kernel,jacobi", [(0, False), (0, True), (3, False), (4, False)])
 def test_full_size_c5g7_2d_sweeps_match_oracle(c5g7_2d_flat, kernel, jacobi):
     """Full-size parity (18.2 M reference segments per group sweep): every group, with and without the coarse-current
     tally, two inners with self scatter on the device, against the C oracle on the same seeded inputs."""
@@ -321,7 +343,7 @@ def test_full_size_c5g7_2d_sweeps_match_oracle(c5g7_2d_flat, kernel, jacobi):
     G, n_reg, bcpg = (int(flat[k][0]) for k in ("n_group", "n_reg", "bc_per_group"))
     rng = np.random.default_rng(2025)
     sw = _sweeper(flat, boundary_update=1 if jacobi else 0, kernel=kernel)
-    assert sw.stats()["kernel"] == (4 if kernel == 0 else kernel)
+    assert sw.stats()["kernel"] == (5 if kernel == 0 else kernel)
     sw.set_xs(0, flat["xs_tr"], xstr_src=flat["xs_tr"], xs_self=flat["xs_self"])
     xy = _xy_mask(flat)
     area = flat["surf_area"]
@@ -365,7 +387,8 @@ def test_full_size_sweep_is_linear_in_source_and_boundary_flux(c5g7_2d_flat):
 
 @pytest.mark.parametrize("case", ["mini2d_gs", "mini3d_gs"])
 @pytest.mark.parametrize("n_inner", [1, 3])
-def test_two_groups_per_call_on_the_chunk_kernel(case, n_inner):
+@pytest.mark.parametrize("kernel", [4, 5])
+def test_two_groups_per_call_on_the_chunk_kernel(case, n_inner, kernel):
     """g_count = 2 keeps one group per warp (chunk kernel, group-major q-bar / tally): equals two single-group calls."""
     flat, gold = load_case(case)
     G, n_reg, n_plane = (int(flat[k][0]) for k in ("n_group", "n_reg", "n_plane"))
@@ -378,7 +401,7 @@ def test_two_groups_per_call_on_the_chunk_kernel(case, n_inner):
     bc = rng.uniform(0.0, 0.3, size=(n_plane, G, bcpg))
     res = []
     for pair in (True, False):
-        sw = _sweeper(flat, boundary_update=0, kernel=4)
+        sw = _sweeper(flat, boundary_update=0, kernel=kernel)
         sw.set_xs(0, xstr, xstr_src=xstr, xs_self=xself)
         sw.set_source(0, src)
         sw.set_flux(0, flux0)
