@@ -35,8 +35,8 @@ struct RcList {
     int P = 0, LMAX = 0, NW = 0, TEAMS = 0, NC = 0, NS = 0;
     int64_t n_slots = 0; // n_batches * NS: positions of the list's attenuation cache per (plane, group)
     int32_t n_batches = 0, n_units = 0, max_nb = 1;
-    int2 *d_units = nullptr, *d_lane_meta = nullptr, *d_bc_slots = nullptr, *d_chunk_trk = nullptr;
-    int32_t *d_slot_fsr = nullptr;
+    int2 *d_units = nullptr, *d_chunk_trk = nullptr;
+    int32_t *d_batch_hdr = nullptr; // per batch: FSR ids of the slots + one int4 per lane (rc_header_ints words)
 };
 
 struct TrackList { // one launch of the track kernel: units of one (unique plane, boundary phase, polar count)
@@ -328,10 +328,10 @@ int build_rc_list(mocb200_sweeper *h, TrackList &tl, const std::vector<ChunkUnit
     if (rc.n_slots >= (int64_t)INT32_MAX)
         return fail(h, MOCB200_ERR_INVALID, "register-chunk kernel: slot count exceeds 32-bit indexing");
 
-    std::vector<int32_t> slot_fsr((size_t)rc.n_slots, -1);
+    // padding slots: a valid FSR id (q-bar is gathered from it; the slot's 1 - e is 0) with the sign bit set
+    std::vector<int32_t> slot_fsr((size_t)rc.n_slots, INT32_MIN);
     std::vector<int2> chunk_trk((size_t)n_batches * NC, make_int2(-1, 0));
-    std::vector<int2> lane_meta((size_t)n_batches * NC * P, make_int2(0, 0));
-    std::vector<int2> bc_slots;
+    std::vector<int4> lane_meta((size_t)n_batches * NC * P, make_int4(0, 0, INT32_MIN, 0));
     for (const Placed &pl : placed) {
         const ChunkUnit &u = cu[pl.unit];
         const bool chained = pl.nch > NCp;
@@ -341,8 +341,9 @@ int build_rc_list(mocb200_sweeper *h, TrackList &tl, const std::vector<ChunkUnit
             const int gchunk   = (pl.batch + (chained ? j / NCp : 0)) * NC + in_batch;
             const int k0       = j * L;
             chunk_trk[gchunk]  = make_int2(pl.unit, k0);
-            for (int k = 0; k < L && k0 + k < u.nseg; k++)
-                slot_fsr[(size_t)gchunk * L + k] = pfsr[(size_t)u.seg_begin + k0 + k];
+            for (int k = 0; k < L; k++)
+                slot_fsr[(size_t)gchunk * L + k] = k0 + k < u.nseg ? pfsr[(size_t)u.seg_begin + k0 + k]
+                                                                   : (pfsr[(size_t)u.seg_begin + u.nseg - 1] | INT32_MIN);
             int flags = 0;
             if (j == 0)
                 flags |= kRcHead;
@@ -353,24 +354,25 @@ int build_rc_list(mocb200_sweeper *h, TrackList &tl, const std::vector<ChunkUnit
             else if (chained && in_batch == NCp - 1)
                 flags |= kRcTailCont;
             for (int q = 0; q < P; q++) {
-                int2 m = make_int2(flags | (u.ang[q] << 8), 0);
-                if (flags & kRcHead) {
-                    m.y = (int)bc_slots.size();
-                    bc_slots.push_back(make_int2(u.in_f[q], u.out_b[q]));
-                } else if (flags & kRcTail) {
-                    m.y = (int)bc_slots.size();
-                    bc_slots.push_back(make_int2(u.in_b[q], u.out_f[q]));
-                }
+                int4 m = make_int4(flags | (u.ang[q] << 8), 0, INT32_MIN, 0);
+                if (flags & kRcHead) // the forward sweep enters here, the backward sweep leaves
+                    m.y = u.in_f[q], m.z = u.out_b[q];
+                else if (flags & kRcTail)
+                    m.y = u.in_b[q], m.z = u.out_f[q];
                 lane_meta[(size_t)gchunk * P + q] = m;
             }
         }
     }
-    if (bc_slots.empty())
-        bc_slots.push_back(make_int2(0, INT32_MIN));
     int rc2;
-    if ((rc2 = dev_upload(h, &rc.d_units, units)) || (rc2 = dev_upload(h, &rc.d_lane_meta, lane_meta)) ||
-        (rc2 = dev_upload(h, &rc.d_bc_slots, bc_slots)) || (rc2 = dev_upload(h, &rc.d_chunk_trk, chunk_trk)) ||
-        (rc2 = dev_upload(h, &rc.d_slot_fsr, slot_fsr)))
+    // one record per batch, fetched by one bulk copy: [NS] FSR ids, [32 NW] lane descriptors
+    const int HS = rc_header_ints(P, L, rc.NW), T = 32 * rc.NW;
+    std::vector<int32_t> hdr((size_t)n_batches * HS, 0);
+    for (int b = 0; b < n_batches; b++) {
+        std::copy(slot_fsr.begin() + (size_t)b * rc.NS, slot_fsr.begin() + (size_t)(b + 1) * rc.NS, hdr.begin() + (size_t)b * HS);
+        std::memcpy(hdr.data() + (size_t)b * HS + rc.NS, lane_meta.data() + (size_t)b * T, (size_t)T * sizeof(int4));
+    }
+    if ((rc2 = dev_upload(h, &rc.d_units, units)) || (rc2 = dev_upload(h, &rc.d_chunk_trk, chunk_trk)) ||
+        (rc2 = dev_upload(h, &rc.d_batch_hdr, hdr)))
         return rc2;
     return MOCB200_OK;
 }
@@ -1664,8 +1666,8 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                                     rc.P, tally, rc.LMAX, rc.NW, rc.TEAMS);
                     RcArgs c{};
                     c.units = rc.d_units, c.n_units = rc.n_units, c.pinfo = tl.d_pinfo, c.n_planes = tl.n_planes;
-                    c.lane_meta = rc.d_lane_meta, c.bc_slots = rc.d_bc_slots, c.chunk_trk = rc.d_chunk_trk;
-                    c.tracks = tl.d_cunits, c.slot_fsr = rc.d_slot_fsr, c.cache = tl.d_cache, c.n_slots = rc.n_slots;
+                    c.chunk_trk = rc.d_chunk_trk;
+                    c.tracks = tl.d_cunits, c.batch_hdr = rc.d_batch_hdr, c.cache = tl.d_cache, c.n_slots = rc.n_slots;
                     c.cache_groups = h->cache_slots, c.cache_g0 = sliding ? g_begin : 0;
                     c.wt_v_st = h->d_wt, c.n_ang = h->n_ang, c.bc_per_group = h->bcpg;
                     c.g_begin = g_begin, c.g_count = g_count, c.GP = h->GP, c.n_reg = h->n_reg;

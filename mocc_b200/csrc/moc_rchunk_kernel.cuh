@@ -49,11 +49,17 @@ __host__ __device__ constexpr int rc_slots(int P, int LMAX, int NW)
 {
     return rc_chunks(P, NW) * LMAX;
 }
+// int32 words of one batch header: FSR ids of the slots + one int4 per lane of the team
+__host__ __device__ constexpr int rc_header_ints(int P, int LMAX, int NW)
+{
+    return rc_slots(P, LMAX, NW) + 4 * 32 * NW;
+}
 // dynamic shared memory of one team: attenuations [NS][P], q-bar [NS], contributions [NS][P] (doubles),
-// FSR ids [3][NS] (int32, triple-buffered); tally variants keep the crossing lists in global memory
+// batch headers [3] (triple-buffered); tally variants keep the crossing lists in global memory
 __host__ __device__ constexpr size_t rc_team_bytes(int P, int LMAX, int NW)
 {
-    return (size_t)rc_slots(P, LMAX, NW) * ((size_t)(2 * P + 1) * sizeof(double) + 3 * sizeof(int32_t));
+    return (size_t)rc_slots(P, LMAX, NW) * (size_t)(2 * P + 1) * sizeof(double) +
+           3 * (size_t)rc_header_ints(P, LMAX, NW) * sizeof(int32_t);
 }
 
 struct RcArgs {
@@ -61,11 +67,14 @@ struct RcArgs {
     int32_t n_units;
     const int2 *pinfo; // per plane of the list: {macroplane, its first FSR}
     int32_t n_planes;
-    const int2 *lane_meta; // per (chunk, polar angle): {flags | sweep angle << 8, index into bc_slots}
-    const int2 *bc_slots;  // per head / tail (chunk, polar angle): {incoming boundary slot, encoded outgoing slot}
     const int2 *chunk_trk; // per chunk: {track (index into tracks), first position of the chunk in its track}
     const ChunkUnit *tracks;
-    const int32_t *slot_fsr; // [n_slots] plane-local FSR id, -1: padding
+    // Per batch one record of rc_header_ints() int32, fetched by ONE bulk copy two items ahead:
+    //   [NS] plane-local FSR id of every slot; padding: a valid id with the sign bit set (q-bar is gathered from
+    //        it -- the slot's 1 - e is 0 --, nothing is tallied)
+    //   [32 NW] int4 per lane (chunk, polar angle): {flags | sweep angle << 8, incoming boundary slot, encoded
+    //        outgoing slot, -}; head chunk = forward in / backward out, tail chunk = backward in / forward out
+    const int32_t *batch_hdr;
     const double *cache;     // attenuation cache of this list [plane][g][slot][P]
     int64_t n_slots;
     int32_t cache_groups, cache_g0;
@@ -102,9 +111,10 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
 {
     static_assert(P == 1 || P == 2 || P == 4, "one lane per polar angle: 1, 2 or 4 lanes per chunk");
     static_assert(LMAX % 2 == 1, "odd chunk length: conflict-free shared-memory strides");
-    constexpr int T  = 32 * NW;             // lanes of a team
-    constexpr int NC = rc_chunks(P, NW);    // chunks per batch
-    constexpr int NS = rc_slots(P, LMAX, NW); // slots per batch
+    constexpr int T  = 32 * NW;                 // lanes of a team
+    constexpr int NC = rc_chunks(P, NW);        // chunks per batch
+    constexpr int NS = rc_slots(P, LMAX, NW);   // slots per batch
+    constexpr int HS = rc_header_ints(P, LMAX, NW); // int32 words of a batch header
     extern __shared__ __align__(16) double s_dyn[];
     __shared__ uint64_t s_bar[4 * TEAMS];
     __shared__ double s_tot[TEAMS][NW][P][4]; // per warp and polar angle: forward map (A, B), backward map (A, B) of the warp's chunks
@@ -119,8 +129,8 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     double *exb   = reinterpret_cast<double *>(wbase);
     double *qb    = exb + (size_t)NS * P;
     double *ab    = qb + NS;
-    int32_t *fbuf = reinterpret_cast<int32_t *>(ab + (size_t)NS * P); // three FSR-id buffers
-    uint64_t *bar = &s_bar[4 * team];                                 // [0..2] FSR-id buffers, [3] attenuations
+    int32_t *fbuf = reinterpret_cast<int32_t *>(ab + (size_t)NS * P); // three batch-header buffers (FSR ids, lane descriptors)
+    uint64_t *bar = &s_bar[4 * team];                                 // [0..2] header buffers, [3] attenuations
     auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(T) : "memory"); };
     if (loader) {
         for (int i = 0; i < 4; i++)
@@ -128,7 +138,7 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     team_sync();
-    uint32_t par_f = 0u, par_e = 0u; // mbarrier phase parities (bit i of par_f: FSR-id buffer i)
+    uint32_t par_f = 0u, par_e = 0u; // mbarrier phase parities (bit i of par_f: header buffer i)
 
     const int GP            = a.GP;
     const uint32_t per_unit = (uint32_t)a.n_planes * (uint32_t)a.g_count;
@@ -143,55 +153,56 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     };
     auto decode = [&](uint32_t w) {
         Item it;
-        const uint32_t unit = w / per_unit;
-        const uint32_t r    = w - unit * per_unit;
-        it.ipl              = (int)(r / (uint32_t)a.g_count);
-        it.grel             = (int)(r - (uint32_t)it.ipl * (uint32_t)a.g_count);
-        const int2 u        = __ldg(a.units + unit);
+        uint32_t unit = w;
+        it.ipl = 0, it.grel = 0;
+        if (per_unit != 1u) {
+            unit             = w / per_unit;
+            const uint32_t r = w - unit * per_unit;
+            it.ipl           = (int)(r / (uint32_t)a.g_count);
+            it.grel          = (int)(r - (uint32_t)it.ipl * (uint32_t)a.g_count);
+        }
+        const int2 u = __ldg(a.units + unit);
         it.batch = u.x, it.nb = u.y;
         const int2 pi = __ldg(a.pinfo + it.ipl);
         it.plane = pi.x, it.first_reg = pi.y;
         return it;
     };
-    auto ex_of = [&](const Item &it, int batch) {
-        const int g = a.g_begin + it.grel;
-        return a.cache + (((size_t)it.ipl * a.cache_groups + (g - a.cache_g0)) * a.n_slots + (size_t)batch * NS) * P;
-    };
     // ---- staging ----
-    auto issue_fsr = [&](int fi, int batch) {
+    auto issue_hdr = [&](int fi, int batch) {
         if (loader) {
-            constexpr uint32_t bytes = (uint32_t)NS * 4u;
+            constexpr uint32_t bytes = (uint32_t)HS * 4u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar + fi, bytes);
-            bulk_g2s(fbuf + fi * NS, a.slot_fsr + (size_t)batch * NS, bytes, bar + fi);
+            bulk_g2s(fbuf + fi * HS, a.batch_hdr + (size_t)batch * HS, bytes, bar + fi);
         }
     };
     auto issue_ex = [&](const Item &it, int batch) {
         if (loader) {
             constexpr uint32_t bytes = (uint32_t)NS * (uint32_t)P * 8u;
+            const int g     = a.g_begin + it.grel;
+            const char *src = reinterpret_cast<const char *>(
+                a.cache + (((size_t)it.ipl * a.cache_groups + (g - a.cache_g0)) * a.n_slots + (size_t)batch * NS) * P);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar + 3, bytes);
-            const char *src = reinterpret_cast<const char *>(ex_of(it, batch));
             for (uint32_t off = 0; off < bytes; off += 16384u)
                 bulk_g2s(reinterpret_cast<char *>(exb) + off, src + off, min(16384u, bytes - off), bar + 3);
         }
     };
+    constexpr int NJ = (NS + T - 1) / T;
     auto gather_q = [&](int fi, const Item &it) { // striped: lanes on consecutive slots
         mbar_wait(bar + fi, (par_f >> fi) & 1u);
         par_f ^= 1u << fi;
-        const double *qf  = a.q + (size_t)it.grel * a.n_reg + it.first_reg;
-        const int32_t *fb = fbuf + fi * NS;
+        const double *qf = a.q + (size_t)it.grel * a.n_reg + it.first_reg;
+        asm volatile("" : "+l"(qf)); // keep the base in a register pair: one IMAD.WIDE per address
+        const int32_t *fb = fbuf + fi * HS;
+        int f[NJ];
 #pragma unroll
-        for (int j = 0; j < (NS + T - 1) / T; j++) {
-            const int i = tl + j * T;
-            if (NS % T == 0 || i < NS) {
-                const int f = fb[i];
-                if (f >= 0)
-                    cp_async_8(qb + i, qf + f);
-                else
-                    qb[i] = 0.0;
-            }
-        }
+        for (int j = 0; j < NJ; j++) // all shared-memory reads first: one latency, not NJ
+            f[j] = (NS % T == 0 || tl + j * T < NS) ? fb[tl + j * T] : 0;
+#pragma unroll
+        for (int j = 0; j < NJ; j++)
+            if (NS % T == 0 || tl + j * T < NS)
+                cp_async_8(qb + tl + j * T, qf + (uint32_t)(f[j] & 0x7fffffff));
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto wait_staged = [&]() {
@@ -201,28 +212,33 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
         team_sync();
     };
     auto reduce_tally = [&](int fi, const Item &it) { // striped again: one red per slot
-        double *tf        = a.tally + (size_t)it.grel * a.n_reg + it.first_reg;
-        const int32_t *fb = fbuf + fi * NS;
+        double *tf = a.tally + (size_t)it.grel * a.n_reg + it.first_reg;
+        asm volatile("" : "+l"(tf));
+        const int32_t *fb = fbuf + fi * HS;
+        int f[NJ];
+        double v[NJ];
 #pragma unroll
-        for (int j = 0; j < (NS + T - 1) / T; j++) {
+        for (int j = 0; j < NJ; j++) {
             const int i = tl + j * T;
+            f[j] = -1, v[j] = 0.0;
             if (NS % T == 0 || i < NS) {
-                const int f = fb[i];
-                double v;
+                f[j] = fb[i];
                 if constexpr (P == 2) {
                     const double2 t = *reinterpret_cast<const double2 *>(ab + 2 * i);
-                    v = t.x + t.y;
+                    v[j] = t.x + t.y;
                 } else if constexpr (P == 4) {
                     const double2 t = *reinterpret_cast<const double2 *>(ab + 4 * i);
                     const double2 u = *reinterpret_cast<const double2 *>(ab + 4 * i + 2);
-                    v = (t.x + t.y) + (u.x + u.y);
+                    v[j] = (t.x + t.y) + (u.x + u.y);
                 } else {
-                    v = ab[i];
+                    v[j] = ab[i];
                 }
-                if (f >= 0)
-                    atomicAdd(tf + f, v);
             }
         }
+#pragma unroll
+        for (int j = 0; j < NJ; j++)
+            if (f[j] >= 0) // explicit state space: a generic atomicAdd on the laundered pointer would be an ATOM with a result
+                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(tf + (uint32_t)f[j]), "d"(v[j]) : "memory");
     };
 
     // ---- the lane's chunk: load once, keep 1 - e and q-bar in registers ----
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     };
     // Scan over the chunks of the team. In: the forward / backward map of the lane's chunk (with the resets of
     // track heads / tails folded in). Out: the flux entering the chunk in both directions (valid for chunks that
-    // are not heads / tails themselves); tf/tb: the team's total maps (chained tracks).
+    // are not heads / tails themselves); team_total: the team's total maps (chained tracks).
     auto scan = [&](const Maps &m, double &psi_f, double &psi_b, Maps *team_total) {
         double EfA = 1.0, EfB = 0.0, EbA = 1.0, EbB = 0.0;
         double TAf = m.Af, TF = m.Bf, TAb = m.Ab, TB = m.Bb;
@@ -343,7 +359,7 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
         const int surf_off = a.plane_surf_offset[it.plane];
         const int g        = a.g_begin + it.grel;
         const int nslot    = 2 * a.n_ang;
-        const int32_t *fb  = fbuf + fi_cur * NS + c * LMAX;
+        const int32_t *fb  = fbuf + fi_cur * HS + c * LMAX; // FSR ids of the lane's chunk
         auto tally_cross = [&](const Cross &x, double psi, int dir) {
             const int norm = x.surf & 1;
             const int surf = x.surf >> 1;
@@ -444,11 +460,20 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     auto load_in = [&](const Item &it, int slot) {
         return a.bc_in[((size_t)it.plane * a.bc_per_group + slot) * GP + (a.g_begin + it.grel)];
     };
+    // lane descriptor of a staged header (its bulk copy has been waited for by gather_q) and the two values it
+    // points to: angle weight, incoming boundary flux (never written by this launch: one boundary phase)
+    auto lane_inputs = [&](int fi, const Item &it, int4 &mt, double &wt_o, double &pin_o) {
+        mt    = *reinterpret_cast<const int4 *>(fbuf + fi * HS + NS + 4 * tl);
+        wt_o  = __ldg(a.wt_v_st + it.plane * a.n_ang + (mt.x >> 8));
+        pin_o = 0.0;
+        if (mt.x & (kRcHead | kRcTail))
+            pin_o = load_in(it, mt.y);
+    };
 
     // ================= pipeline over the work items of this team (static round-robin) =================
-    // Invariant at the top of a single-batch item `cur` with `staged`: its FSR ids are in buffer fi, its attenuations
-    // and q-bar are on their way, its lane descriptors are in registers; if the next item is a single batch too,
-    // its FSR ids have been requested into buffer (fi + 1) % 3.
+    // Invariant at the top of a single-batch item `cur` with `staged`: its header is in buffer fi, its attenuations
+    // and q-bar are on their way, its lane descriptor, angle weight and incoming boundary flux are in registers (or
+    // on their way); if the next item is a single batch too, its header has been requested into buffer (fi + 1) % 3.
     uint32_t w_cur = team_global;
     if (w_cur >= total)
         return;
@@ -457,50 +482,45 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     Item nxt{};
     if (w_nxt < total)
         nxt = decode(w_nxt);
-    int fi = 0; // FSR-id buffer of `cur`
-    int2 meta = make_int2(0, 0), bcs = make_int2(0, INT32_MIN);
+    int fi = 0; // header buffer of `cur`
+    int4 meta = make_int4(0, 0, INT32_MIN, 0);
+    double wt = 0.0, pin = 0.0;
     bool staged = false;
     double *sc  = a.scratch + (size_t)team_global * a.scratch_per_team;
 
     while (true) {
         const bool have_nxt = w_nxt < total;
         if (!staged && cur.nb == 1) { // (re)start the pipeline at `cur`
-            meta = __ldg(a.lane_meta + (size_t)cur.batch * NC * P + tl);
-            bcs  = (meta.x & (kRcHead | kRcTail)) ? __ldg(a.bc_slots + meta.y) : make_int2(0, INT32_MIN);
-            issue_fsr(fi, cur.batch);
+            issue_hdr(fi, cur.batch);
             issue_ex(cur, cur.batch);
             if (have_nxt && nxt.nb == 1)
-                issue_fsr((fi + 1) % 3, nxt.batch);
+                issue_hdr((fi + 1) % 3, nxt.batch);
             gather_q(fi, cur);
+            lane_inputs(fi, cur, meta, wt, pin);
             staged = true;
         }
         if (cur.nb == 1) {
             // ---------------- one batch: the common case ----------------
-            const int flags = meta.x & 0xff;
-            const bool head = flags & kRcHead, tail = flags & kRcTail;
-            const double wt = __ldg(a.wt_v_st + cur.plane * a.n_ang + (meta.x >> 8));
-            double pin = 0.0;
-            if (head || tail)
-                pin = load_in(cur, bcs.x);
-            const int out_enc = bcs.y;
+            const bool head = meta.x & kRcHead, tail = meta.x & kRcTail;
+            const bool pre  = have_nxt && nxt.nb == 1;
+            const uint32_t w_nn = w_nxt + n_teams;
+            Item nn{};
+            if (have_nxt && w_nn < total) // two items ahead: its descriptor loads fly during compose
+                nn = decode(w_nn);
             wait_staged();
             double ome[LMAX], qv[LMAX];
             Maps m = compose(ome, qv);
             team_sync(); // attenuation and q-bar buffers are free; everybody has left the previous reduction
-            // the next item: attenuations, q-bar (its FSR ids were requested one item earlier), lane descriptors;
-            // the item after it: FSR ids
-            const bool pre = have_nxt && nxt.nb == 1;
-            const uint32_t w_nn = w_nxt + n_teams;
-            Item nn{};
-            if (have_nxt && w_nn < total)
-                nn = decode(w_nn);
-            int2 meta_n = make_int2(0, 0);
+            // the next item: attenuations, q-bar, angle weight and incoming flux (its header was requested one item
+            // earlier); the item after it: header
+            int4 meta_n = make_int4(0, 0, INT32_MIN, 0);
+            double wt_n = 0.0, pin_n = 0.0;
             if (pre) {
                 issue_ex(nxt, nxt.batch);
                 if (w_nn < total && nn.nb == 1)
-                    issue_fsr((fi + 2) % 3, nn.batch);
+                    issue_hdr((fi + 2) % 3, nn.batch);
                 gather_q((fi + 1) % 3, nxt);
-                meta_n = __ldg(a.lane_meta + (size_t)nxt.batch * NC * P + tl);
+                lane_inputs((fi + 1) % 3, nxt, meta_n, wt_n, pin_n);
             }
             if (head)
                 m.Bf = fma(m.Af, pin, m.Bf), m.Af = 0.0;
@@ -512,27 +532,24 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
                 psi_f = pin;
             if (tail)
                 psi_b = pin;
-            int2 bcs_n = make_int2(0, INT32_MIN);
-            if (pre && (meta_n.x & (kRcHead | kRcTail)))
-                bcs_n = __ldg(a.bc_slots + meta_n.y);
             if constexpr (TALLY == 0)
                 walk(ome, qv, wt, psi_f, psi_b);
             else
                 walk_tally(ome, qv, wt, psi_f, psi_b, cur, cur.batch, fi, meta.x >> 8);
             if (tail)
-                store_exit(cur, out_enc, psi_f);
+                store_exit(cur, meta.z, psi_f);
             if (head)
-                store_exit(cur, out_enc, psi_b);
+                store_exit(cur, meta.z, psi_b);
             team_sync(); // contributions complete
             reduce_tally(fi, cur);
             if (!have_nxt)
                 break;
             if (pre) {
                 fi = (fi + 1) % 3;
-                meta = meta_n, bcs = bcs_n;
+                meta = meta_n, wt = wt_n, pin = pin_n;
             } else {
                 staged = false;
-                team_sync(); // the chained unit that follows reuses the buffers at once
+                team_sync(); // what follows reuses the buffers at once
             }
             w_cur = w_nxt, cur = nxt, w_nxt = w_nn, nxt = nn;
         } else {
@@ -541,23 +558,23 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
             // of the track (b == 0) or continues the forward sweep with the flux the team carries, its last chunk is
             // the tail of the track (b == nb - 1) or continues the backward sweep with the flux pass A left in `sc`.
             const int nb = cur.nb;
-            auto stage_block = [&](int b, int2 &mt, int2 &bs) {
-                mt = __ldg(a.lane_meta + (size_t)(cur.batch + b) * NC * P + tl);
-                bs = (mt.x & (kRcHead | kRcTail)) ? __ldg(a.bc_slots + mt.y) : make_int2(0, INT32_MIN);
-                issue_fsr(fi, cur.batch + b);
+            auto stage_block = [&](int b, int4 &mt) {
+                team_sync(); // the previous block's reduction has left the buffers
+                issue_hdr(fi, cur.batch + b);
                 issue_ex(cur, cur.batch + b);
                 gather_q(fi, cur);
+                mt = *reinterpret_cast<const int4 *>(fbuf + fi * HS + NS + 4 * tl);
                 wait_staged();
             };
             // pass A, highest sub-block first: the backward flux entering sub-block b - 1 from above
             for (int b = nb - 1; b >= 1; --b) {
-                int2 mt, bs;
-                stage_block(b, mt, bs);
+                int4 mt;
+                stage_block(b, mt);
                 double ome[LMAX], qv[LMAX];
                 Maps m = compose(ome, qv);
                 const int flags = mt.x & 0xff;
                 if (flags & kRcTail) // the tail of the track: incoming boundary flux
-                    m.Bb = fma(m.Ab, load_in(cur, bs.x), m.Bb), m.Ab = 0.0;
+                    m.Bb = fma(m.Ab, load_in(cur, mt.y), m.Bb), m.Ab = 0.0;
                 if (flags & kRcTailCont) // written by this loop's previous trip
                     m.Bb = fma(m.Ab, sc[b * P + p], m.Bb), m.Ab = 0.0;
                 double pf, pb;
@@ -565,24 +582,23 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
                 scan(m, pf, pb, &tot);
                 if (tl < P) // the total backward map has A = 0 (a tail was folded in): B is the flux leaving below
                     sc[(b - 1) * P + p] = tot.Bb;
-                team_sync();
             }
             // pass B, lowest sub-block first: forward chain, both walks, tally
             double cfk = 0.0;
             for (int b = 0; b < nb; ++b) {
-                int2 mt, bs;
-                stage_block(b, mt, bs);
-                const int flags = mt.x & 0xff;
-                const double wt = __ldg(a.wt_v_st + cur.plane * a.n_ang + (mt.x >> 8));
+                int4 mt;
+                stage_block(b, mt);
+                const int flags  = mt.x & 0xff;
+                const double wtb = __ldg(a.wt_v_st + cur.plane * a.n_ang + (mt.x >> 8));
                 double ome[LMAX], qv[LMAX];
                 Maps m = compose(ome, qv);
                 const bool head = flags & kRcHead, tail = flags & kRcTail;
                 const bool start_f = flags & (kRcHead | kRcHeadCont), start_b = flags & (kRcTail | kRcTailCont);
                 double pin_f = 0.0, pin_b = 0.0;
                 if (start_f)
-                    pin_f = head ? load_in(cur, bs.x) : cfk;
+                    pin_f = head ? load_in(cur, mt.y) : cfk;
                 if (start_b)
-                    pin_b = tail ? load_in(cur, bs.x) : sc[b * P + p];
+                    pin_b = tail ? load_in(cur, mt.y) : sc[b * P + p];
                 if (start_f)
                     m.Bf = fma(m.Af, pin_f, m.Bf), m.Af = 0.0;
                 if (start_b)
@@ -595,18 +611,18 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
                 if (start_b)
                     psi_b = pin_b;
                 if constexpr (TALLY == 0)
-                    walk(ome, qv, wt, psi_f, psi_b);
+                    walk(ome, qv, wtb, psi_f, psi_b);
                 else
-                    walk_tally(ome, qv, wt, psi_f, psi_b, cur, cur.batch + b, fi, mt.x >> 8);
+                    walk_tally(ome, qv, wtb, psi_f, psi_b, cur, cur.batch + b, fi, mt.x >> 8);
                 if (tail)
-                    store_exit(cur, bs.y, psi_f);
+                    store_exit(cur, mt.z, psi_f);
                 if (head)
-                    store_exit(cur, bs.y, psi_b);
+                    store_exit(cur, mt.z, psi_b);
                 cfk = tot.Bf; // forward flux leaving the sub-block (total A = 0: a head was folded in)
                 team_sync();
                 reduce_tally(fi, cur);
-                team_sync();
             }
+            team_sync();
             if (!have_nxt)
                 break;
             w_cur = w_nxt, cur = nxt;
@@ -617,7 +633,6 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
         }
     }
 }
-
 
 // Fills the attenuation cache of a packed list for groups [g_begin, g_begin + g_count): the same table
 // lookup of -xstr*len/sin(theta) as exp_cache_kernel (exponential.hpp:69-79), one thread per slot; padding
@@ -650,6 +665,7 @@ template <int P> __global__ void __launch_bounds__(512, 1) rc_cache_kernel(const
     const double space  = (a.exp_max - a.exp_min) / (double)a.exp_n;
     const double rspace = 1.0 / space;
     const double c0     = -a.exp_min * rspace;
+    const double xmax   = (double)a.exp_n;
     const int64_t total = a.n_slots * a.n_planes;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int ipl     = (int)(i / a.n_slots);
@@ -685,7 +701,7 @@ template <int P> __global__ void __launch_bounds__(512, 1) rc_cache_kernel(const
                 const double xs = a.xstr[(size_t)reg * a.GP + g];
 #pragma unroll
                 for (int p = 0; p < P; p++)
-                    ex[p] = exp_interp(s_tab, xs * len[p] * nrs[p], c0, rspace);
+                    ex[p] = exp_interp(s_tab, xs * len[p] * nrs[p], c0, rspace, xmax);
             } else {
 #pragma unroll
                 for (int p = 0; p < P; p++)

@@ -150,11 +150,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // table entries, same interpolant. The interval index is obtained with a round-down add
 // instead of a double->int conversion and the interpolation weight as x - floor(x); both
 // differ from the reference's operation order by O(1e-15) relative (continuity at the
-// knots makes an index flip at an interval boundary harmless).
-__device__ __forceinline__ double exp_interp(const double *__restrict__ tab, double v, double c0, double rspace)
+// knots makes an index flip at an interval boundary harmless). Arguments outside the table
+// [vmin, vmax] (x < 0 or x > xmax = N; a non-positive cross section under transverse-leakage
+// splitting gives v > 0) fall back to exp() as the reference does (exponential.hpp:71-75, minus its print).
+__device__ __forceinline__ double exp_interp(const double *__restrict__ tab, double v, double c0, double rspace,
+                                             double xmax)
 {
     const double x = fma(v, rspace, c0); // (v - vmin) * rspace
-    if (x < 0.0)                         // v < vmin: the reference falls back to std::exp
+    if (x < 0.0 || x > xmax)
         return exp(v);
     const double magic = 4503599627370496.0; // 2^52
     const double xi    = __dadd_rd(x, magic);
@@ -186,6 +189,7 @@ static __global__ void __launch_bounds__(kWarpBlock, 1) sweep_warp_kernel(const 
     __shared__ uint64_t s_bar;
 
     double c0 = 0.0, rspace = 0.0;
+    const double xmax = (double)a.exp_n;
     if (!CACHED) {
         if (threadIdx.x == 0) {
             mbar_init(&s_bar, 1);
@@ -375,7 +379,7 @@ static __global__ void __launch_bounds__(kWarpBlock, 1) sweep_warp_kernel(const 
                     q[c]             = v.y;
 #pragma unroll
                     for (int p = 0; p < P; p++) {
-                        const double x = exp_interp(s_dyn, t * nrs[p], c0, rspace);
+                        const double x = exp_interp(s_dyn, t * nrs[p], c0, rspace, xmax);
                         ex[p][c]       = valid ? x : 1.0;
                     }
                 }
@@ -683,6 +687,7 @@ template <int P> __global__ void __launch_bounds__(512, 1) exp_cache_kernel(cons
     const double space  = (a.exp_max - a.exp_min) / (double)a.exp_n;
     const double rspace = 1.0 / space;
     const double c0     = -a.exp_min * rspace;
+    const double xmax   = (double)a.exp_n;
     const int lane      = threadIdx.x & 31;
     const int warps     = gridDim.x * (blockDim.x >> 5);
     const int64_t total = (int64_t)a.n_units * a.n_planes;
@@ -712,7 +717,7 @@ template <int P> __global__ void __launch_bounds__(512, 1) exp_cache_kernel(cons
                 double ex[P];
 #pragma unroll
                 for (int p = 0; p < P; p++)
-                    ex[p] = valid ? exp_interp(s_tab, xs * len[p] * nrs[p], c0, rspace) : 1.0;
+                    ex[p] = valid ? exp_interp(s_tab, xs * len[p] * nrs[p], c0, rspace, xmax) : 1.0;
                 if (a.group_major) { // [plane][g][pos][P]: the P values of a position are contiguous
                     double *dst = a.cache + (((size_t)ipl * a.cache_groups + (g - a.cache_g0)) * a.list_pseg + u.cpos + k) * P;
                     if constexpr (P == 2) {

@@ -44,6 +44,30 @@ bool same_ray(const Ray &a, const Ray &b)
 }
 }
 
+// One reference Ray (ray.hpp:33-216) -> one track of the flat arrays: boundary slots, the coarse cells / surfaces
+// it starts from in either direction, segment lengths and FSR ids in forward order, packed RayCoarseData records.
+void append_ray(FlatProblem &fp, const mocc::moc::Ray &ray)
+{
+    if (fp.trk_seg_begin.empty())
+        fp.trk_seg_begin.push_back(0);
+    if (fp.trk_cm_begin.empty())
+        fp.trk_cm_begin.push_back(0);
+    fp.trk_bc.push_back(ray.bc(0));
+    fp.trk_bc.push_back(ray.bc(1));
+    fp.trk_cm_start.push_back((int)ray.cm_cell_fw());
+    fp.trk_cm_start.push_back((int)ray.cm_cell_bw());
+    fp.trk_cm_start.push_back((int)ray.cm_surf_fw());
+    fp.trk_cm_start.push_back((int)ray.cm_surf_bw());
+    for (int is = 0; is < ray.nseg(); is++) {
+        fp.seg_len.push_back(ray.seg_len(is));
+        fp.seg_fsr.push_back((int)ray.seg_index(is));
+    }
+    for (int ic = 0; ic < ray.ncseg(); ic++)
+        fp.cm_data.push_back(pack_cm(ray, ic));
+    fp.trk_seg_begin.push_back((int64_t)fp.seg_len.size());
+    fp.trk_cm_begin.push_back((int64_t)fp.cm_data.size());
+}
+
 FlatProblem flatten(const mocc::CoreMesh &mesh, const mocc::moc::RayData &rays,
                     const std::vector<int> &macroplane_unique_ids,
                     const std::vector<int> &first_reg_macroplane, const double *vol,
@@ -206,22 +230,8 @@ FlatProblem flatten(const mocc::CoreMesh &mesh, const mocc::moc::RayData &rays,
     for (int u = 0; u < fp.n_unique; u++) {
         for (int gi = 0; gi < fp.n_geom; gi++) {
             const auto &ang_rays = rays[u][geom_first[gi]];
-            for (const auto &ray : ang_rays) {
-                fp.trk_bc.push_back(ray.bc(0));
-                fp.trk_bc.push_back(ray.bc(1));
-                fp.trk_cm_start.push_back((int)ray.cm_cell_fw());
-                fp.trk_cm_start.push_back((int)ray.cm_cell_bw());
-                fp.trk_cm_start.push_back((int)ray.cm_surf_fw());
-                fp.trk_cm_start.push_back((int)ray.cm_surf_bw());
-                for (int is = 0; is < ray.nseg(); is++) {
-                    fp.seg_len.push_back(ray.seg_len(is));
-                    fp.seg_fsr.push_back((int)ray.seg_index(is));
-                }
-                for (int ic = 0; ic < ray.ncseg(); ic++)
-                    fp.cm_data.push_back(pack_cm(ray, ic));
-                fp.trk_seg_begin.push_back((int64_t)fp.seg_len.size());
-                fp.trk_cm_begin.push_back((int64_t)fp.cm_data.size());
-            }
+            for (const auto &ray : ang_rays)
+                append_ray(fp, ray);
             fp.geom_trk_begin.push_back((int64_t)fp.trk_bc.size() / 2);
         }
     }

@@ -22,6 +22,7 @@ class CoreMesh;
 class AngularQuadrature;
 namespace moc {
 class RayData;
+class Ray;
 }
 }
 
@@ -59,6 +60,9 @@ struct FlatProblem {
     ArrayFile to_arrayfile() const;
     static FlatProblem from_arrayfile(const ArrayFile &af);
 };
+
+// Appends one reference Ray as one track (what flatten() does for every ray of every geometry class)
+void append_ray(FlatProblem &fp, const mocc::moc::Ray &ray);
 
 // vol: FSR volumes as TransportSweeper::vol_ holds them (MeshTreatment::PLANE)
 FlatProblem flatten(const mocc::CoreMesh &mesh, const mocc::moc::RayData &rays,

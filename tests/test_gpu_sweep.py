@@ -208,6 +208,31 @@ def test_batched_groups_match_oracle(case, jacobi, kernel):
     sw.close()
 
 
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
+def test_exponential_arguments_outside_the_table_match_oracle(kernel):
+    """Exponential_Linear falls back to std::exp outside [-10, 0] (exponential.hpp:71-75): an optically thick
+    region (tau > 10) and a NEGATIVE transport cross section (possible under transverse-leakage splitting:
+    argument > 0) must both go through that branch, not through an out-of-range table read."""
+    flat, gold = load_case("mini2d_gs")
+    n_reg, n_plane, bcpg = int(flat["n_reg"][0]), int(flat["n_plane"][0]), int(flat["bc_per_group"][0])
+    rng = np.random.default_rng(11)
+    xstr = gold["xs_tr_0"].copy()
+    xstr[::7] = 60.0    # tau up to ~70 per segment: below the table
+    xstr[3::11] = -0.02  # above the table
+    qbar = rng.uniform(0.05, 1.0, size=n_reg)
+    bc = rng.uniform(0.0, 0.3, size=(n_plane, bcpg))
+    sw = _sweeper(flat, boundary_update=0, kernel=kernel)
+    sw.set_xs(0, xstr)
+    sw.set_qbar(0, qbar)
+    for ip in range(n_plane):
+        sw.set_boundary(ip, 0, bc[ip])
+    sw.sweep(0, 1, n_inner=1, tally_mode=0, use_qbar=True)
+    f_o, bc_o, _, _ = oracle_sweep1g(flat, xstr, qbar, bc, gs_boundary=True, tally_mode=0)
+    _close(sw.get_flux(0, 1)[0], f_o, rtol=1e-10)
+    _close(np.stack([sw.get_boundary(ip, 0, 1)[0] for ip in range(n_plane)]), bc_o, rtol=1e-10)
+    sw.close()
+
+
 @pytest.mark.parametrize("kernel", [2, 3, 4, -4, 5, -5])
 @pytest.mark.parametrize("max_polar", [1, 2])
 def test_corrections_match_reference_golden(kernel, max_polar):

@@ -6,8 +6,12 @@ rep, kern, skip, mangled = sys.argv[1:5]
 lib = sys.argv[5] if len(sys.argv) > 5 else os.path.join(os.path.dirname(__file__), '..', 'mocc_b200', 'csrc', 'libmocc_b200.so')
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith('.cubin')):  # one cubin per translation unit
+    d = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    if mangled in d:
+        dis = d.splitlines()
+        break
 lines_of = []  # per instruction: (file, line)
 infn = False; cur = ('?', 0)
 for ln in dis:
@@ -54,7 +58,7 @@ def text(f, l):
     return ''
 print('total samples', tot)
 for key, c in sorted(agg.items(), key=lambda kv: (kv[0][0], kv[0][1])):
-    if c['samples'] < tot * 0.004:
+    if c['samples'] < tot * float(os.environ.get('NCU_MIN_FRAC', '0.004')):
         continue
     top = ', '.join(f'{k}:{v}' for k, v in c.most_common(6) if k not in ('samples', 'inst') and v > 0)
     print(f"{key[0][:22]:22s}:{key[1]:4d} {c['samples']:5d} {100*c['samples']/tot:5.1f}% inst {c['inst']:8d} | {text(*key)[:60]:60s} | {top}")
