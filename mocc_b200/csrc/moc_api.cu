@@ -35,7 +35,7 @@ struct RcList {
     int P = 0, LMAX = 0, NW = 0, TEAMS = 0, NC = 0, NS = 0;
     int64_t n_slots = 0; // n_batches * NS: positions of the list's attenuation cache per (plane, group)
     int32_t n_batches = 0, n_units = 0, max_nb = 1;
-    int2 *d_units = nullptr, *d_chunk_trk = nullptr;
+    int2 *d_units = nullptr, *d_chunk_trk = nullptr, *d_pinfo = nullptr; // d_pinfo: {macroplane, start in the regrouped layout}
     int32_t *d_batch_hdr = nullptr; // per batch: FSR ids of the slots + one int4 per lane (rc_header_ints words)
 };
 
@@ -112,7 +112,9 @@ struct mocb200_sweeper {
     std::vector<bool> cache_valid; // per group
     int cache_slots = 0;           // groups the group-major cache holds at once (G when everything fits)
     int cache_g0 = 0, cache_gn = 0; // groups resident when cache_slots < G: [cache_g0, cache_g0 + cache_gn)
-    double *d_qg = nullptr, *d_tg = nullptr; // group-major q-bar / tally [G][n_reg]
+    double *d_qg = nullptr, *d_tg = nullptr; // group-major q-bar / tally [G][n_reg] ([G][n_regp], regrouped FSRs: RCHUNK)
+    int32_t *d_fsr_perm = nullptr;           // RCHUNK: FSR -> position in the regrouped layout
+    int n_regp = 0;
     // 2D3D correction factors
     bool have_corr = false;
     std::string corr_why; // why MOCB200_TALLY_CORRECTIONS is unavailable
@@ -241,29 +243,155 @@ void build_crossings(const mocb200_problem &p, int64_t t, int nseg, std::vector<
 }
 
 // ---- register-chunk kernel: launch geometry and batch packing ----
-bool rc_config_known(const RcConfig &c)
+RcFn pick_rc_kernel(int np, int tally, const RcConfig &c); // below
+
+constexpr int kRcSmemBudget = 232448 - 4096; // opt-in dynamic shared memory per CTA minus the static part
+
+bool rc_config_fits(int np, const RcConfig &c)
 {
-    return pick_rc_kernel_p2(0, c) != nullptr;
+    return pick_rc_kernel(np, 0, c) != nullptr && (size_t)c.TEAMS * rc_team_bytes(np, c.LMAX, c.NW) <= (size_t)kRcSmemBudget;
 }
 
-// default: long chunks while the longest track still fits one batch, else the chained path takes the few longest
+// Launch geometry of a list. Measured on C5G7-2D (profiles/r2/tuning.md): the longest chunks that still leave the
+// kernel without register spills win (13 slots: least scan work per slot), and three four-warp teams without spills
+// beat four with. More lanes per chunk (polar angles) mean fewer chunks per batch: eight-warp teams then keep the
+// long tracks inside one batch (a chained unit is not pipelined).
 RcConfig rc_pick_config(int np, int max_nseg)
 {
     static const char *force = getenv("MOCB200_RC_CFG"); // tuning hook: "LMAX,NW,TEAMS"
     if (force) {
         RcConfig c{0, 0, 0};
-        if (sscanf(force, "%d,%d,%d", &c.LMAX, &c.NW, &c.TEAMS) == 3 && rc_config_known(c))
+        if (sscanf(force, "%d,%d,%d", &c.LMAX, &c.NW, &c.TEAMS) == 3 && rc_config_fits(np, c))
             return c;
     }
-    (void)np;
-    (void)max_nseg;
-    return RcConfig{11, 4, 4};
+    const RcConfig pref[] = {{13, 4, 3}, {13, 8, 2}, {13, 4, 2}, {11, 4, 3}, {11, 4, 2}, {7, 4, 4}};
+    const RcConfig *first = nullptr;
+    for (const RcConfig &c : pref) {
+        if (!rc_config_fits(np, c))
+            continue;
+        if (!first)
+            first = &c;
+        if (max_nseg <= rc_slots(np, c.LMAX, c.NW))
+            return c;
+    }
+    return first ? *first : RcConfig{7, 4, 4};
+}
+
+// Regroups the FSRs of one unique plane so that FSRs which rays visit within a few consecutive segments share
+// 32-byte sectors (4 doubles) of the q-bar / tally arrays: the striped gather and reduction of the register-chunk
+// kernel then touch ~14 instead of ~23 sectors per 32 slots on C5G7-2D (both are bound by sectors per request).
+// Two rounds of heavy-edge matching on the co-occurrence graph (pairs, then pairs of pairs); groups of 4 first
+// (sector-aligned), smaller groups after them. Returns new plane-local id per original plane-local id.
+std::vector<int32_t> build_fsr_groups(const mocb200_problem &p, int u, int nreg)
+{
+    const int64_t t0 = p.geom_trk_begin[(size_t)u * p.n_geom], t1 = p.geom_trk_begin[(size_t)(u + 1) * p.n_geom];
+    const int64_t nseg_u = p.trk_seg_begin[t1] - p.trk_seg_begin[t0];
+    const int64_t stride = std::max<int64_t>(1, nseg_u * 3 / 24000000); // sample the tracks of very large planes
+    struct Edge {
+        int32_t a, b;
+        float w;
+    };
+    auto collect = [&](auto &&emit) {
+        for (int64_t t = t0; t < t1; t += stride) {
+            const int64_t s0 = p.trk_seg_begin[t], n = p.trk_seg_begin[t + 1] - s0;
+            for (int64_t k = 0; k < n; k++)
+                for (int d = 1; d <= 3 && k + d < n; d++) {
+                    const int32_t x = p.seg_fsr[s0 + k], y = p.seg_fsr[s0 + k + d];
+                    if (x != y)
+                        emit(std::min(x, y), std::max(x, y));
+                }
+        }
+    };
+    // weighted edge list via an open-addressing table (key = a * nreg + b)
+    auto edges_of = [&](int n_nodes, auto &&for_each_pair) {
+        size_t cap = 1u << 16;
+        std::vector<uint64_t> keys(cap, UINT64_MAX);
+        std::vector<float> wts(cap, 0.f);
+        size_t used = 0;
+        auto rehash = [&]() {
+            std::vector<uint64_t> k2(cap * 4, UINT64_MAX);
+            std::vector<float> w2(cap * 4, 0.f);
+            for (size_t i = 0; i < cap; i++)
+                if (keys[i] != UINT64_MAX) {
+                    size_t j = (keys[i] * 0x9E3779B97F4A7C15ull) >> 20 & (cap * 4 - 1);
+                    while (k2[j] != UINT64_MAX)
+                        j = (j + 1) & (cap * 4 - 1);
+                    k2[j] = keys[i], w2[j] = wts[i];
+                }
+            keys.swap(k2), wts.swap(w2), cap *= 4;
+        };
+        for_each_pair([&](int32_t a, int32_t b, float w) {
+            const uint64_t key = (uint64_t)a * (uint64_t)n_nodes + (uint64_t)b;
+            size_t j = (key * 0x9E3779B97F4A7C15ull) >> 20 & (cap - 1);
+            while (keys[j] != UINT64_MAX && keys[j] != key)
+                j = (j + 1) & (cap - 1);
+            if (keys[j] == UINT64_MAX) {
+                keys[j] = key;
+                if (++used * 2 > cap) {
+                    wts[j] += w;
+                    rehash();
+                    return;
+                }
+            }
+            wts[j] += w;
+        });
+        std::vector<Edge> e;
+        e.reserve(used);
+        for (size_t i = 0; i < cap; i++)
+            if (keys[i] != UINT64_MAX)
+                e.push_back({(int32_t)(keys[i] / (uint64_t)n_nodes), (int32_t)(keys[i] % (uint64_t)n_nodes), wts[i]});
+        return e;
+    };
+    auto match = [](int n_nodes, std::vector<Edge> &e, std::vector<int32_t> &super) { // returns number of supernodes
+        std::stable_sort(e.begin(), e.end(), [](const Edge &x, const Edge &y) {
+            return x.w != y.w ? x.w > y.w : (x.a != y.a ? x.a < y.a : x.b < y.b); // deterministic
+        });
+        std::vector<int32_t> mate(n_nodes, -1);
+        for (const Edge &x : e)
+            if (mate[x.a] < 0 && mate[x.b] < 0)
+                mate[x.a] = x.b, mate[x.b] = x.a;
+        super.assign(n_nodes, -1);
+        int ns = 0;
+        for (int r = 0; r < n_nodes; r++)
+            if (super[r] < 0) {
+                super[r] = ns;
+                if (mate[r] >= 0)
+                    super[mate[r]] = ns;
+                ns++;
+            }
+        return ns;
+    };
+    std::vector<Edge> e1 = edges_of(nreg, [&](auto &&add) { collect([&](int32_t a, int32_t b) { add(a, b, 1.f); }); });
+    std::vector<int32_t> pair_of, quad_of;
+    const int n_pair = match(nreg, e1, pair_of);
+    std::vector<Edge> e2 = edges_of(n_pair, [&](auto &&add) {
+        for (const Edge &x : e1) {
+            const int32_t a = pair_of[x.a], b = pair_of[x.b];
+            if (a != b)
+                add(std::min(a, b), std::max(a, b), x.w);
+        }
+    });
+    const int n_quad = match(n_pair, e2, quad_of);
+    // members of every group in original order; full groups first (sector-aligned), each class in order of its
+    // lowest original id (keeps neighbouring pins in neighbouring cache lines)
+    std::vector<std::vector<int32_t>> members(n_quad);
+    for (int r = 0; r < nreg; r++)
+        members[quad_of[pair_of[r]]].push_back(r);
+    std::vector<int32_t> perm(nreg, 0);
+    int32_t next = 0;
+    for (int pass = 0; pass < 2; pass++)
+        for (int g = 0; g < n_quad; g++)
+            if ((members[g].size() == 4) == (pass == 0))
+                for (int32_t r : members[g])
+                    perm[r] = next++;
+    return perm;
 }
 
 // Cuts the tracks of a list (cu: longest first) into chunks of LMAX slots and packs them into batches of NC
 // chunks such that no track straddles a batch (best fit, decreasing); a track with more than NC chunks takes
 // consecutive batches of its own (chained unit). Uploads the per-slot / per-lane tables the kernel reads.
-int build_rc_list(mocb200_sweeper *h, TrackList &tl, const std::vector<ChunkUnit> &cu, const std::vector<int32_t> &pfsr)
+int build_rc_list(mocb200_sweeper *h, TrackList &tl, const std::vector<ChunkUnit> &cu, const std::vector<int32_t> &pfsr,
+                  const std::vector<int32_t> &lperm, const std::vector<int2> &pinfo_rc, const std::vector<Cross> &xcross)
 {
     RcList &rc = tl.rc;
     const RcConfig cfg = rc_pick_config(tl.np, tl.max_nseg);
@@ -342,8 +470,8 @@ int build_rc_list(mocb200_sweeper *h, TrackList &tl, const std::vector<ChunkUnit
             const int k0       = j * L;
             chunk_trk[gchunk]  = make_int2(pl.unit, k0);
             for (int k = 0; k < L; k++)
-                slot_fsr[(size_t)gchunk * L + k] = k0 + k < u.nseg ? pfsr[(size_t)u.seg_begin + k0 + k]
-                                                                   : (pfsr[(size_t)u.seg_begin + u.nseg - 1] | INT32_MIN);
+                slot_fsr[(size_t)gchunk * L + k] = k0 + k < u.nseg ? lperm[pfsr[(size_t)u.seg_begin + k0 + k]]
+                                                                   : (lperm[pfsr[(size_t)u.seg_begin + u.nseg - 1]] | INT32_MIN);
             int flags = 0;
             if (j == 0)
                 flags |= kRcHead;
@@ -364,15 +492,42 @@ int build_rc_list(mocb200_sweeper *h, TrackList &tl, const std::vector<ChunkUnit
         }
     }
     int rc2;
-    // one record per batch, fetched by one bulk copy: [NS] FSR ids, [32 NW] lane descriptors
+    // one record per batch, fetched by one bulk copy: [NS] FSR ids, [32 NW] lane descriptors, [NC] tally descriptors
     const int HS = rc_header_ints(P, L, rc.NW), T = 32 * rc.NW;
     std::vector<int32_t> hdr((size_t)n_batches * HS, 0);
+    const int32_t any_sentinel = (int32_t)xcross.size() - 1; // the lists end with sentinels
+    auto lower_bound = [&](int32_t begin, int32_t n, int node) { // first index with xcross[i].node >= node
+        int32_t a0 = 0, a1 = n;
+        while (a0 < a1) {
+            const int32_t m = (a0 + a1) >> 1;
+            if (xcross[(size_t)begin + m].node < node)
+                a0 = m + 1;
+            else
+                a1 = m;
+        }
+        return begin + a0;
+    };
     for (int b = 0; b < n_batches; b++) {
-        std::copy(slot_fsr.begin() + (size_t)b * rc.NS, slot_fsr.begin() + (size_t)(b + 1) * rc.NS, hdr.begin() + (size_t)b * HS);
-        std::memcpy(hdr.data() + (size_t)b * HS + rc.NS, lane_meta.data() + (size_t)b * T, (size_t)T * sizeof(int4));
+        int32_t *rec = hdr.data() + (size_t)b * HS;
+        std::copy(slot_fsr.begin() + (size_t)b * rc.NS, slot_fsr.begin() + (size_t)(b + 1) * rc.NS, rec);
+        std::memcpy(rec + rc.NS, lane_meta.data() + (size_t)b * T, (size_t)T * sizeof(int4));
+        int32_t *td = rec + rc.NS + 4 * T;
+        for (int ch = 0; ch < NC; ch++, td += 8) {
+            const int2 ct = chunk_trk[(size_t)b * NC + ch];
+            td[0] = td[1] = any_sentinel;
+            if (ct.x < 0)
+                continue;
+            const ChunkUnit &u = cu[ct.x];
+            const int k0 = ct.y, kt_end = std::min(k0 + L, u.nseg);
+            if (kt_end > k0) {
+                td[0] = lower_bound(u.cross_begin, u.n_fw, k0);
+                td[1] = lower_bound(u.cross_begin + u.n_fw + 1, u.n_bw, u.nseg - kt_end);
+            }
+            td[2] = u.nseg, td[3] = k0, td[4] = u.seg_begin + k0;
+        }
     }
     if ((rc2 = dev_upload(h, &rc.d_units, units)) || (rc2 = dev_upload(h, &rc.d_chunk_trk, chunk_trk)) ||
-        (rc2 = dev_upload(h, &rc.d_batch_hdr, hdr)))
+        (rc2 = dev_upload(h, &rc.d_batch_hdr, hdr)) || (rc2 = dev_upload(h, &rc.d_pinfo, pinfo_rc)))
         return rc2;
     return MOCB200_OK;
 }
@@ -672,6 +827,37 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
             (rc2 = dev_upload(h, &h->d_xptr, xptr)) || (rc2 = dev_upload(h, &h->d_xcross, xcross)))
             return rc2;
 
+        // register-chunk kernel: regrouped FSR numbering (per unique plane) and the padded plane starts of its
+        // q-bar / tally layout (every plane starts on a sector boundary)
+        std::vector<std::vector<int32_t>> rc_lperm(p.n_unique);
+        std::vector<int32_t> rc_plane_start(p.n_plane + 1, 0);
+        if (h->kernel == MOCB200_KERNEL_RCHUNK) {
+            std::vector<int32_t> perm((size_t)p.n_reg, 0);
+            for (int ip = 0; ip < p.n_plane; ip++) {
+                const int nreg_pl = (ip + 1 < p.n_plane ? p.plane_first_reg[ip + 1] : p.n_reg) - p.plane_first_reg[ip];
+                rc_plane_start[ip + 1] = rc_plane_start[ip] + ((nreg_pl + 3) & ~3);
+                const int u = p.plane_unique[ip];
+                if (ip < h->plane_begin || ip >= h->plane_end)
+                    continue;
+                if (rc_lperm[u].empty()) {
+                    static const char *no_group = getenv("MOCB200_RC_NOGROUP"); // tuning hook: keep the reference numbering
+                    if (no_group && no_group[0] == '1') {
+                        rc_lperm[u].resize(nreg_pl);
+                        for (int r = 0; r < nreg_pl; r++)
+                            rc_lperm[u][r] = r;
+                    } else {
+                        rc_lperm[u] = build_fsr_groups(p, u, nreg_pl);
+                    }
+                }
+                if ((int)rc_lperm[u].size() != nreg_pl)
+                    return fail(h, MOCB200_ERR_INVALID, "planes of one unique geometry differ in their FSR count");
+                for (int r = 0; r < nreg_pl; r++)
+                    perm[(size_t)p.plane_first_reg[ip] + r] = rc_plane_start[ip] + rc_lperm[u][r];
+            }
+            h->n_regp = rc_plane_start[p.n_plane];
+            if ((rc2 = dev_upload(h, &h->d_fsr_perm, perm)))
+                return rc2;
+        }
         for (int u = 0; u < p.n_unique; u++) {
             std::vector<int32_t> planes;
             for (int ip = h->plane_begin; ip < h->plane_end; ip++)
@@ -770,8 +956,13 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                             pinfo.push_back(make_int2(ip, p.plane_first_reg[ip]));
                         if ((rc2 = dev_upload(h, &tl.d_cunits, cu)) || (rc2 = dev_upload(h, &tl.d_pinfo, pinfo)))
                             return rc2;
-                        if (h->kernel == MOCB200_KERNEL_RCHUNK && (rc2 = build_rc_list(h, tl, cu, pfsr)))
-                            return rc2;
+                        if (h->kernel == MOCB200_KERNEL_RCHUNK) {
+                            std::vector<int2> pinfo_rc;
+                            for (int32_t ip : planes)
+                                pinfo_rc.push_back(make_int2(ip, rc_plane_start[ip]));
+                            if ((rc2 = build_rc_list(h, tl, cu, pfsr, rc_lperm[u], pinfo_rc, xcross)))
+                                return rc2;
+                        }
                     }
                     h->tlists.push_back(tl);
                 }
@@ -967,7 +1158,8 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
         return rc;
     h->have_xs.assign(p.n_group, false);
     h->cache_valid.assign(p.n_group, false);
-    if ((rc = dev_alloc(h, &h->d_qg, (size_t)p.n_group * p.n_reg)) || (rc = dev_alloc(h, &h->d_tg, (size_t)p.n_group * p.n_reg)))
+    const size_t n_qg = (size_t)p.n_group * std::max(p.n_reg, h->n_regp);
+    if ((rc = dev_alloc(h, &h->d_qg, n_qg)) || (rc = dev_alloc(h, &h->d_tg, n_qg)))
         return rc;
     h->stats.device_bytes = h->device_bytes;
     h->stats.kernel       = h->kernel;
@@ -1063,6 +1255,9 @@ ChunkFn pick_chunk_kernel(int np, int nw, int tally)
 typedef void (*RcCacheFn)(const RcCacheArgs);
 
 // the instantiations live in moc_rc_p{1,2,4}.cu (one translation unit per lane count, compiled in parallel)
+// the tallying sweeps need more registers per thread: one team less per CTA when that instantiation exists
+RcConfig rc_tally_config(int np, int tally, const RcConfig &c);
+
 RcFn pick_rc_kernel(int np, int tally, const RcConfig &c)
 {
     switch (np) {
@@ -1071,6 +1266,14 @@ RcFn pick_rc_kernel(int np, int tally, const RcConfig &c)
     case 4: return pick_rc_kernel_p4(tally, c);
     }
     return nullptr;
+}
+
+RcConfig rc_tally_config(int np, int tally, const RcConfig &c)
+{
+    if (tally == 0 || c.TEAMS <= 3) // three four-warp teams leave 168 registers per thread: no spills
+        return c;
+    const RcConfig t{c.LMAX, c.NW, c.TEAMS - 1};
+    return (t.TEAMS >= 1 && pick_rc_kernel(np, tally, t)) ? t : c;
 }
 
 RcCacheFn pick_rc_cache_kernel(int np)
@@ -1271,9 +1474,11 @@ int mocb200_create(const mocb200_problem *prob, const mocb200_options *opt, mocb
         for (const auto &tl : h->tlists) {
             const RcList &rc = tl.rc;
             const RcConfig cfg{rc.LMAX, rc.NW, rc.TEAMS};
-            for (int t = 0; t < 3 && e == cudaSuccess; t++)
-                e = cudaFuncSetAttribute((const void *)pick_rc_kernel(rc.P, t, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(rc.TEAMS * rc_team_bytes(rc.P, rc.LMAX, rc.NW)));
+            for (int t = 0; t < 3 && e == cudaSuccess; t++) {
+                const RcConfig ct = rc_tally_config(rc.P, t, cfg);
+                e = cudaFuncSetAttribute((const void *)pick_rc_kernel(rc.P, t, ct), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(ct.TEAMS * rc_team_bytes(rc.P, rc.LMAX, rc.NW)));
+            }
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute((const void *)pick_rc_cache_kernel(rc.P), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         }
@@ -1576,7 +1781,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_xstr,
                 h->d_qbar, group_major ? h->d_qg : h->d_qbar, cached ? nullptr : h->d_xq,
                 group_major ? h->d_tg : h->d_tally, group_major ? 1 : 0, use_qbar ? 0 : 1, h->d_counters,
-                h->n_counters <= 256 ? h->n_counters : 0);
+                h->n_counters <= 256 ? h->n_counters : 0, rchunk ? h->d_fsr_perm : nullptr, h->n_regp);
             h->stats.kernel_launches++;
         }
         if (tally != MOCB200_TALLY_NONE) {
@@ -1659,13 +1864,14 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 a.exp_table = h->d_exp, a.exp_n = h->exp_n, a.exp_min = h->exp_min, a.exp_max = h->exp_max;
                 if (rchunk) {
                     const RcList &rc = tl.rc;
-                    const RcConfig cfg{rc.LMAX, rc.NW, rc.TEAMS};
+                    const RcConfig cfg = rc_tally_config(rc.P, tally, RcConfig{rc.LMAX, rc.NW, rc.TEAMS});
                     RcFn fn = pick_rc_kernel(rc.P, tally, cfg);
                     if (!fn)
                         return fail(h, MOCB200_ERR_INVALID, "register-chunk kernel: no instantiation for P %d tally %d (%d,%d,%d)",
                                     rc.P, tally, rc.LMAX, rc.NW, rc.TEAMS);
                     RcArgs c{};
-                    c.units = rc.d_units, c.n_units = rc.n_units, c.pinfo = tl.d_pinfo, c.n_planes = tl.n_planes;
+                    c.units = rc.d_units, c.n_units = rc.n_units, c.pinfo = rc.d_pinfo, c.n_planes = tl.n_planes;
+                    c.plane_first_reg = h->d_plane_first_reg, c.seg_fsr = h->d_pseg_fsr, c.n_regp = h->n_regp;
                     c.chunk_trk = rc.d_chunk_trk;
                     c.tracks = tl.d_cunits, c.batch_hdr = rc.d_batch_hdr, c.cache = tl.d_cache, c.n_slots = rc.n_slots;
                     c.cache_groups = h->cache_slots, c.cache_g0 = sliding ? g_begin : 0;
@@ -1677,8 +1883,8 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                     c.plane_surf_offset = h->d_plane_surf_offset, c.current = h->d_current, c.surface_flux = h->d_surfflux;
                     c.dsum = h->d_dsum, c.ssum = h->d_ssum, c.n_surf_plane = h->n_surf_plane, c.n_plane_total = h->n_plane;
                     const int64_t items = (int64_t)rc.n_units * tl.n_planes * g_count;
-                    const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>((items + rc.TEAMS - 1) / rc.TEAMS, h->sm_count));
-                    fn<<<rgrid, 32 * rc.NW * rc.TEAMS, rc.TEAMS * rc_team_bytes(rc.P, rc.LMAX, rc.NW), h->stream>>>(c);
+                    const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>((items + cfg.TEAMS - 1) / cfg.TEAMS, h->sm_count));
+                    fn<<<rgrid, 32 * rc.NW * cfg.TEAMS, cfg.TEAMS * rc_team_bytes(rc.P, rc.LMAX, rc.NW), h->stream>>>(c);
                 } else if (h->kernel == MOCB200_KERNEL_CHUNK && gl == 1) {
                     int caps = 0, nw = 1, teams = 1;
                     const bool tl_tally = tally != MOCB200_TALLY_NONE;
@@ -1742,11 +1948,12 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         if (fuse_q && !last)
             finalize_next_q_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
                 h->n_reg, h->GP, g_begin, g_count, h->d_tg, h->d_xstr, h->d_vol, h->d_qbar, h->d_flux, h->reg_lo,
-                h->reg_hi, h->d_src, h->d_xs_self, h->d_xstr_src, h->d_qg, h->d_counters, h->n_counters);
+                h->reg_hi, h->d_src, h->d_xs_self, h->d_xstr_src, h->d_qg, h->d_counters, h->n_counters,
+                rchunk ? h->d_fsr_perm : nullptr, h->n_regp);
         else
             finalize_flux_q_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
                 h->n_reg, h->GP, g_begin, g_count, group_major ? h->d_tg : h->d_tally, h->d_xstr, h->d_vol, h->d_qbar,
-                h->d_flux, h->reg_lo, h->reg_hi, group_major ? 1 : 0);
+                h->d_flux, h->reg_lo, h->reg_hi, group_major ? 1 : 0, rchunk ? h->d_fsr_perm : nullptr, h->n_regp);
         h->stats.kernel_launches++;
         CUDA_TRY(h, cudaGetLastError());
     }

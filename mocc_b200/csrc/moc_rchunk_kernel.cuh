@@ -49,10 +49,15 @@ __host__ __device__ constexpr int rc_slots(int P, int LMAX, int NW)
 {
     return rc_chunks(P, NW) * LMAX;
 }
-// int32 words of one batch header: FSR ids of the slots + one int4 per lane of the team
-__host__ __device__ constexpr int rc_header_ints(int P, int LMAX, int NW)
+// int32 words of one batch header: FSR ids of the slots + one int4 per lane of the team (what the plain sweep
+// copies) + two int4 per chunk for the tallying sweeps
+__host__ __device__ constexpr int rc_header_ints_plain(int P, int LMAX, int NW)
 {
     return rc_slots(P, LMAX, NW) + 4 * 32 * NW;
+}
+__host__ __device__ constexpr int rc_header_ints(int P, int LMAX, int NW)
+{
+    return rc_header_ints_plain(P, LMAX, NW) + 8 * rc_chunks(P, NW);
 }
 // dynamic shared memory of one team: attenuations [NS][P], q-bar [NS], contributions [NS][P] (doubles),
 // batch headers [3] (triple-buffered); tally variants keep the crossing lists in global memory
@@ -65,23 +70,31 @@ __host__ __device__ constexpr size_t rc_team_bytes(int P, int LMAX, int NW)
 struct RcArgs {
     const int2 *units; // {first batch, batches}: swept by one team (batches > 1: one track longer than a batch)
     int32_t n_units;
-    const int2 *pinfo; // per plane of the list: {macroplane, its first FSR}
+    const int2 *pinfo; // per plane of the list: {macroplane, start of its FSRs in the regrouped q-bar / tally layout}
     int32_t n_planes;
+    const int32_t *plane_first_reg; // original FSR numbering (TALLY 2: psi_diff sums per FSR)
+    const int32_t *seg_fsr;         // padded segment arrays, original plane-local FSR ids (TALLY 2)
     const int2 *chunk_trk; // per chunk: {track (index into tracks), first position of the chunk in its track}
     const ChunkUnit *tracks;
     // Per batch one record of rc_header_ints() int32, fetched by ONE bulk copy two items ahead:
-    //   [NS] plane-local FSR id of every slot; padding: a valid id with the sign bit set (q-bar is gathered from
-    //        it -- the slot's 1 - e is 0 --, nothing is tallied)
+    //   [NS] plane-local FSR id of every slot IN THE REGROUPED NUMBERING (FSRs that rays visit together share
+    //        32-byte sectors: build_fsr_groups in moc_api.cu); padding: a valid id with the sign bit set (q-bar is
+    //        gathered from it -- the slot's 1 - e is 0 --, nothing is tallied)
     //   [32 NW] int4 per lane (chunk, polar angle): {flags | sweep angle << 8, incoming boundary slot, encoded
     //        outgoing slot, -}; head chunk = forward in / backward out, tail chunk = backward in / forward out
+    //   [NC] 2 x int4 per chunk, copied by the tallying sweeps only: {first forward crossing at or after the
+    //        chunk's first node, first backward crossing at or after its last node (indices into `cross`), segments
+    //        of its track (0: empty chunk), its first position in the track}, {its first position in the padded
+    //        segment arrays (original FSR ids), -, -, -}
     const int32_t *batch_hdr;
     const double *cache;     // attenuation cache of this list [plane][g][slot][P]
     int64_t n_slots;
     int32_t cache_groups, cache_g0;
     const double *wt_v_st; // [n_plane][n_ang]
     int32_t n_ang, bc_per_group;
-    int32_t g_begin, g_count, GP, n_reg;
-    const double *q; // group-major [g - g_begin][n_reg]
+    int32_t g_begin, g_count, GP, n_reg; // n_reg: FSRs of the original numbering (dsum); n_regp: stride of q / tally
+    int32_t n_regp;
+    const double *q; // group-major [g - g_begin][n_regp], regrouped numbering
     double *tally;   // same layout
     const double *bc_in;
     double *bc_out;
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     // ---- staging ----
     auto issue_hdr = [&](int fi, int batch) {
         if (loader) {
-            constexpr uint32_t bytes = (uint32_t)HS * 4u;
+            constexpr uint32_t bytes = (uint32_t)(TALLY ? HS : rc_header_ints_plain(P, LMAX, NW)) * 4u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar + fi, bytes);
             bulk_g2s(fbuf + fi * HS, a.batch_hdr + (size_t)batch * HS, bytes, bar + fi);
@@ -192,7 +205,7 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     auto gather_q = [&](int fi, const Item &it) { // striped: lanes on consecutive slots
         mbar_wait(bar + fi, (par_f >> fi) & 1u);
         par_f ^= 1u << fi;
-        const double *qf = a.q + (size_t)it.grel * a.n_reg + it.first_reg;
+        const double *qf = a.q + (size_t)it.grel * a.n_regp + it.first_reg;
         asm volatile("" : "+l"(qf)); // keep the base in a register pair: one IMAD.WIDE per address
         const int32_t *fb = fbuf + fi * HS;
         int f[NJ];
@@ -212,7 +225,7 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
         team_sync();
     };
     auto reduce_tally = [&](int fi, const Item &it) { // striped again: one red per slot
-        double *tf = a.tally + (size_t)it.grel * a.n_reg + it.first_reg;
+        double *tf = a.tally + (size_t)it.grel * a.n_regp + it.first_reg;
         asm volatile("" : "+l"(tf));
         const int32_t *fb = fbuf + fi * HS;
         int f[NJ];
@@ -323,21 +336,23 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
         psi_f = fma(EfA, cf, EfB);
         psi_b = fma(EbA, cb, EbB);
     };
-    // both walks from registers (kernel:103-129); contributions of the lane's polar angle to ab[slot][p]
+    // both walks from registers (kernel:103-129); contributions of the lane's polar angle to ab[slot][p].
+    // psi' = psi - (psi - q)(1 - e) as ONE dependent DADD + DFMA per slot (the reference's DADD, DMUL, DADD rounds
+    // the product once more: 1e-16 relative); the tallied difference (psi - q)(1 - e) is computed off the chain
     auto walk = [&](const double (&ome)[LMAX], const double (&qv)[LMAX], double wt, double &psi_f, double &psi_b) {
         double s[LMAX];
 #pragma unroll
         for (int k = 0; k < LMAX; k++) {
-            const double d = (psi_f - qv[k]) * ome[k];
-            psi_f -= d;
-            s[k] = d * wt;
+            const double t = psi_f - qv[k];
+            psi_f = fma(-t, ome[k], psi_f);
+            s[k]  = (t * ome[k]) * wt;
         }
         double *al = ab + (size_t)c * LMAX * P + p;
 #pragma unroll
         for (int k = LMAX - 1; k >= 0; k--) {
-            const double d = (psi_b - qv[k]) * ome[k];
-            psi_b -= d;
-            al[k * P] = fma(d, wt, s[k]);
+            const double t = psi_b - qv[k];
+            psi_b     = fma(-t, ome[k], psi_b);
+            al[k * P] = fma(t * ome[k], wt, s[k]);
         }
     };
     // The walks of the last inner: as `walk`, plus moc::Current::post_ray (moc_current_worker.hpp:202-264) or
@@ -345,110 +360,100 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     // the lane's chunk, for the lane's own polar angle (sweep angle `ang`).
     auto walk_tally = [&](const double (&ome)[LMAX], const double (&qv)[LMAX], double wt, double &psi_f, double &psi_b,
                           const Item &it, int batch, int fi_cur, int ang) {
-        const int2 ct = __ldg(a.chunk_trk + (size_t)batch * NC + c);
-        const int k0  = ct.y;
-        int nseg = 0, n_fw = 0, n_bw = 0;
-        const Cross *xfl = a.cross, *xbl = a.cross;
-        if (ct.x >= 0) {
-            const ChunkUnit &u = a.tracks[ct.x];
-            nseg = u.nseg, n_fw = u.n_fw, n_bw = u.n_bw;
-            xfl = a.cross + u.cross_begin, xbl = xfl + n_fw + 1;
-        }
+        (void)batch;
+        const int32_t *tdp = fbuf + fi_cur * HS + NS + 4 * T + 8 * c; // the chunk's tally descriptor
+        const int4 td      = *reinterpret_cast<const int4 *>(tdp);
+        const int nseg = td.z, k0 = td.w;
+        const Cross *xfl = a.cross + td.x, *xbl = a.cross + td.y; // first crossings of the chunk, either direction
         const size_t wo  = ((size_t)it.plane * a.n_ang + ang) * 2;
         const double cw0 = a.cur_w[wo], cw1 = a.cur_w[wo + 1], fw0 = a.flx_w[wo], fw1 = a.flx_w[wo + 1];
         const int surf_off = a.plane_surf_offset[it.plane];
         const int g        = a.g_begin + it.grel;
         const int nslot    = 2 * a.n_ang;
-        const int32_t *fb  = fbuf + fi_cur * HS + c * LMAX; // FSR ids of the lane's chunk
+        // psi_diff sums are kept per FSR of the ORIGINAL numbering (corrections_kernel reads them)
+        const int32_t *fo = a.seg_fsr + (TALLY == 2 ? tdp[4] : 0);
+        const int reg0    = TALLY == 2 ? a.plane_first_reg[it.plane] : 0;
+        double *cur_g = a.current + (size_t)surf_off * GP + g, *sfl_g = a.surface_flux + (size_t)surf_off * GP + g;
+        double *ssum_g = nullptr;
+        if (TALLY == 2)
+            ssum_g = a.ssum + (size_t)it.grel * a.n_plane_total * a.n_ang * a.n_surf_plane * 2 +
+                     ((size_t)it.plane * a.n_ang + ang) * a.n_surf_plane * 2;
         auto tally_cross = [&](const Cross &x, double psi, int dir) {
-            const int norm = x.surf & 1;
-            const int surf = x.surf >> 1;
-            const size_t o = (size_t)(surf + surf_off) * GP + g;
-            const double cs = psi * (norm ? cw1 : cw0), fs = psi * (norm ? fw1 : fw0);
+            const bool ynorm = x.surf & 1;
+            const uint32_t surf = (uint32_t)x.surf >> 1;
+            const double cs = psi * (ynorm ? cw1 : cw0), fs = psi * (ynorm ? fw1 : fw0);
             // forward adds, backward subtracts (moc_current_worker.hpp:230-231); the corrections worker also
             // subtracts the backward SURFACE FLUX (correction_worker.hpp:136-137, 194-195)
-            atomicAdd(&a.current[o], dir ? -cs : cs);
-            atomicAdd(&a.surface_flux[o], (dir && TALLY == 2) ? -fs : fs);
-            if (TALLY == 2) {
-                const size_t so = (size_t)it.grel * a.n_plane_total * a.n_ang * a.n_surf_plane * 2 +
-                                  (((size_t)it.plane * a.n_ang + ang) * a.n_surf_plane + surf) * 2 + dir;
-                atomicAdd(&a.ssum[so], psi);
-            }
+            atomicAdd(cur_g + surf * (uint32_t)GP, dir ? -cs : cs);
+            atomicAdd(sfl_g + surf * (uint32_t)GP, (dir && TALLY == 2) ? -fs : fs);
+            if (TALLY == 2)
+                atomicAdd(ssum_g + surf * 2u + dir, psi);
         };
         auto dsum_add = [&](int f, int dir, double d) {
-            const size_t o = (size_t)it.grel * a.n_reg * nslot + (size_t)(f + it.first_reg) * nslot + ang * 2 + dir;
+            const size_t o = (size_t)it.grel * a.n_reg * nslot + (size_t)(f + reg0) * nslot + ang * 2 + dir;
             atomicAdd(&a.dsum[o], d);
         };
-        auto lower_bound = [](const Cross *l, int n, int node) {
-            int a0 = 0, a1 = n; // first index with l[i].node >= node (the sentinel at n has node INT32_MAX)
-            while (a0 < a1) {
-                const int m = (a0 + a1) >> 1;
-                if (l[m].node < node)
-                    a0 = m + 1;
-                else
-                    a1 = m;
-            }
-            return a0;
-        };
-        const int kt_end = min(k0 + LMAX, nseg); // track positions [k0, kt_end) are real
-        const bool any   = kt_end > k0;
+        // Positions [0, len) of the chunk are real. A forward crossing at track node n is tallied in front of position
+        // n (by the chunk that holds it) or, n == nseg, behind the last position of the track: relative node
+        // rf = n - k0 in [0, len), or len when the chunk ends the track. A backward crossing after nb walked segments
+        // is tallied in front of position nseg - 1 - nb: rb = nseg - 1 - nb - k0 in [0, len), or -1 (nb == nseg:
+        // behind position 0 of the track, k0 == 0). Padding slots leave the flux as it is, so the far-end checks may
+        // sit on them. Crossings outside the chunk are switched off by a node no position compares equal to.
+        const int len    = max(min(LMAX, nseg - k0), 0);
+        const int lim_f  = (k0 + len == nseg) ? len : len - 1; // highest relative node this chunk tallies, forward
         int ci_f = 0, ci_b = 0;
+        int rf = INT32_MAX, rb = INT32_MIN;
         Cross xf{INT32_MAX, 0}, xb{INT32_MAX, 0};
-        if (any) {
-            ci_f = lower_bound(xfl, n_fw, k0);
-            ci_b = lower_bound(xbl, n_bw, nseg - kt_end);
-            xf = xfl[ci_f], xb = xbl[ci_b];
+        auto set_f = [&]() {
+            const int r = xf.node - k0;
+            rf          = (xf.node != INT32_MAX && r <= lim_f) ? r : INT32_MAX;
+        };
+        auto set_b = [&]() {
+            const int r = nseg - 1 - xb.node - k0; // -1 is the near end only for node == nseg (else: the chunk below)
+            rb          = (xb.node != INT32_MAX && (r >= 0 || (r == -1 && xb.node == nseg))) ? r : INT32_MIN;
+        };
+        if (len > 0) {
+            xf = xfl[0], xb = xbl[0];
+            set_f();
+            set_b();
         }
         double s[LMAX];
 #pragma unroll
         for (int k = 0; k < LMAX; k++) {
-            const int kt     = k0 + k; // the forward flux at the node in front of position kt
-            const bool valid = kt < kt_end;
-            if (valid) {
-                while (xf.node == kt) {
-                    tally_cross(xf, psi_f, 0);
-                    xf = xfl[++ci_f];
-                }
+            while (rf == k) { // the forward flux at the node in front of position k
+                tally_cross(xf, psi_f, 0);
+                xf = xfl[++ci_f];
+                set_f();
             }
             const double d = (psi_f - qv[k]) * ome[k];
             psi_f -= d;
             s[k] = d * wt;
-            if (valid) {
-                if (TALLY == 2)
-                    dsum_add(fb[k], 0, d);
-                if (kt == nseg - 1) { // far end of the ray
-                    while (xf.node == nseg) {
-                        tally_cross(xf, psi_f, 0);
-                        xf = xfl[++ci_f];
-                    }
-                }
-            }
+            if (TALLY == 2 && k < len)
+                dsum_add(fo[k], 0, d);
+        }
+        while (rf == LMAX) { // far end of the ray behind a full last chunk
+            tally_cross(xf, psi_f, 0);
+            xf = xfl[++ci_f];
+            set_f();
         }
         double *al = ab + (size_t)c * LMAX * P + p;
 #pragma unroll
         for (int k = LMAX - 1; k >= 0; k--) {
-            const int kt     = k0 + k;
-            const bool valid = kt < kt_end;
-            if (valid) {
-                const int nbw = nseg - 1 - kt; // segments walked by the backward sweep so far
-                while (xb.node == nbw) {
-                    tally_cross(xb, psi_b, 1);
-                    xb = xbl[++ci_b];
-                }
+            while (rb == k) {
+                tally_cross(xb, psi_b, 1);
+                xb = xbl[++ci_b];
+                set_b();
             }
             const double d = (psi_b - qv[k]) * ome[k];
             psi_b -= d;
             al[k * P] = fma(d, wt, s[k]);
-            if (valid) {
-                if (TALLY == 2)
-                    dsum_add(fb[k], 1, d);
-                if (kt == 0) { // near end of the ray
-                    while (xb.node == nseg) {
-                        tally_cross(xb, psi_b, 1);
-                        xb = xbl[++ci_b];
-                    }
-                }
-            }
+            if (TALLY == 2 && k < len)
+                dsum_add(fo[k], 1, d);
+        }
+        while (rb == -1) { // near end of the ray
+            tally_cross(xb, psi_b, 1);
+            xb = xbl[++ci_b];
+            set_b();
         }
     };
     auto store_exit = [&](const Item &it, int enc, double v) {

@@ -748,7 +748,8 @@ static __global__ void self_scatter_q_kernel(int n_reg, int GP, int g_begin, int
                                       const double *__restrict__ xstr_src, const double *__restrict__ xstr,
                                       double *qbar, double *q_out, double2 *__restrict__ xq,
                                       double *__restrict__ tally_out, int group_major, int compute_q,
-                                      uint32_t *__restrict__ counters, int n_counters)
+                                      uint32_t *__restrict__ counters, int n_counters,
+                                      const int32_t *__restrict__ perm = nullptr, int n_regp = 0)
 {
     if (blockIdx.x == 0 && (int)threadIdx.x < n_counters) // work counters of the sweep kernels that follow
         counters[threadIdx.x] = 0u;
@@ -772,7 +773,8 @@ static __global__ void self_scatter_q_kernel(int n_reg, int GP, int g_begin, int
         } else {
             q = qbar[o];
         }
-        const size_t oo = group_major ? (size_t)gi * n_reg + r : o;
+        // group-major layout of the register-chunk kernel: FSRs regrouped so that FSRs visited together share 32-byte sectors
+        const size_t oo = group_major ? (perm ? (size_t)gi * n_regp + perm[r] : (size_t)gi * n_reg + r) : o;
         if (xq)
             xq[o] = make_double2(xstr[o], q);
         else
@@ -785,7 +787,8 @@ static __global__ void self_scatter_q_kernel(int n_reg, int GP, int g_begin, int
 static __global__ void finalize_flux_q_kernel(int n_reg, int GP, int g_begin, int g_count, const double *__restrict__ tally,
                                        const double *__restrict__ xstr, const double *__restrict__ vol,
                                        const double *__restrict__ qbar, double *__restrict__ flux, int reg_lo,
-                                       int reg_hi, int group_major)
+                                       int reg_hi, int group_major, const int32_t *__restrict__ perm = nullptr,
+                                       int n_regp = 0)
 {
     const int nr    = reg_hi - reg_lo;
     const int64_t n = (int64_t)nr * g_count;
@@ -800,7 +803,7 @@ static __global__ void finalize_flux_q_kernel(int n_reg, int GP, int g_begin, in
         }
         const int g     = g_begin + gi;
         const size_t o  = (size_t)r * GP + g;
-        const size_t oo = group_major ? (size_t)gi * n_reg + r : o;
+        const size_t oo = group_major ? (perm ? (size_t)gi * n_regp + perm[r] : (size_t)gi * n_reg + r) : o;
         flux[o] = __dadd_rn(__ddiv_rn(tally[oo], __dmul_rn(xstr[o], vol[r])), __dmul_rn(qbar[o], kFPi));
     }
 }
@@ -813,7 +816,8 @@ static __global__ void finalize_next_q_kernel(int n_reg, int GP, int g_begin, in
                                        double *__restrict__ qbar, double *__restrict__ flux, int reg_lo, int reg_hi,
                                        const double *__restrict__ src, const double *__restrict__ xs_self,
                                        const double *__restrict__ xstr_src, double *__restrict__ q_out,
-                                       uint32_t *__restrict__ counters, int n_counters)
+                                       uint32_t *__restrict__ counters, int n_counters,
+                                       const int32_t *__restrict__ perm = nullptr, int n_regp = 0)
 {
     if (blockIdx.x == 0 && (int)threadIdx.x < n_counters)
         counters[threadIdx.x] = 0u;
@@ -824,7 +828,7 @@ static __global__ void finalize_next_q_kernel(int n_reg, int GP, int g_begin, in
         const int r     = reg_lo + (int)(i - (int64_t)gi * nr);
         const int g     = g_begin + gi;
         const size_t o  = (size_t)r * GP + g;
-        const size_t oo = (size_t)gi * n_reg + r;
+        const size_t oo = perm ? (size_t)gi * n_regp + perm[r] : (size_t)gi * n_reg + r;
         const double f  = __dadd_rn(__ddiv_rn(tally[oo], __dmul_rn(xstr[o], vol[r])), __dmul_rn(qbar[o], kFPi));
         flux[o]         = f;
         const double r_fpi_tr = __ddiv_rn(1.0, __dmul_rn(xstr_src[o], kFPi));
