@@ -17,9 +17,13 @@ updates (S = reference segment count, polar copies counted).
   mode    pergroup: one mocb200_sweep per group (the reference's sweep(group) contract,
           Gauss-Seidel in energy); batched: all groups in one mocb200_sweep (8 group lanes)
 
-With N > 1 (torchrun, one rank per GPU) every rank owns one axial plane of an N-plane stack
-of C5G7 planes -- the plane sharding the 2D3D method uses; planes are independent inside a
-sweep, so there is no data-path collective (scaling "weak").
+With N > 1 (torchrun, one rank per GPU) the problem is ONE stack of N C5G7 planes (N macroplanes of one
+geometry, the plane sharding the 2D3D method uses); rank r creates its handle with plane_begin = r,
+plane_end = r + 1. Planes are independent inside a sweep (no collective in `value`); the e2e leg adds what
+the host solver needs after every sweep(group): the ranks' flux and coarse current / surface-flux slices,
+packed on the device (mocb200_pack_results_device) and exchanged with ONE NCCL all-gather per sweep(group),
+then copied to every rank's pinned host memory; `comm` reports the device time of those all-gathers
+(scaling "weak": one plane per GPU).
 
 --impl reference times the UNMODIFIED reference CPU sweeper (oracle/_ref/ref_tool, OpenMP on
 all host cores) on the same input; rank 0 only.
@@ -101,6 +105,33 @@ def workload_config(name, mode, boundary, S, n_reg, G, n_inner, world):
     return {"workload": WORKLOADS[name][0] + (f"; {world} axial planes, one per GPU" if world > 1 else ""),
             "mode": mode, "boundary_update": boundary, "segments": int(S), "n_reg": int(n_reg), "groups": int(G),
             "n_inner": int(n_inner), "updates_per_step": 2.0 * S * G * n_inner * world, "l2": L2_NOTE}
+
+
+def stack_planes(arr, n):
+    """An n-plane problem out of a one-plane one: n macroplanes sharing the plane's ray data (unique geometry 0),
+    FSRs / coarse cells / coarse surfaces numbered plane by plane as Mesh does (mesh.cpp:88-136)."""
+    if n == 1:
+        return arr
+    assert int(arr["n_plane"][0]) == 1
+    out = dict(arr)
+    R, ncp, nsp = int(arr["n_reg"][0]), int(arr["n_cell_plane"][0]), int(arr["n_surf_plane"][0])
+    i32 = lambda v: np.array([v], dtype=np.int32)  # noqa: E731
+    out["n_plane"], out["nz"], out["n_reg"] = i32(n), i32(n), i32(n * R)
+    out["n_cell"], out["n_surf"] = i32(n * ncp), i32(n * nsp + ncp)
+    for k in ("wt_v_st", "cur_wx", "cur_wy", "flx_wx", "flx_wy", "plane_height", "plane_dz", "vol"):
+        out[k] = np.tile(arr[k], n)
+    out["plane_unique"] = np.zeros(n, dtype=np.int32)
+    out["plane_first_reg"] = (np.arange(n) * R).astype(np.int32)
+    out["plane_cell_offset"] = (np.arange(n) * ncp).astype(np.int32)
+    out["plane_xs_offset"] = (np.arange(n) * ncp).astype(np.int32)
+    out["plane_surf_offset"] = (np.arange(n) * nsp).astype(np.int32)
+    out["surf_area"] = np.concatenate([np.tile(arr["surf_area"][:nsp], n), arr["surf_area"][nsp:]])
+    out["n_seg_reference"] = arr["n_seg_reference"] * n
+    out["n_ray_reference"] = arr["n_ray_reference"] * n
+    for k in ("xs_tr", "xs_self", "xs_nf", "xs_ch"):
+        out[k] = np.tile(arr[k], (1, n))
+    out["xs_scat"] = np.tile(arr["xs_scat"], (1, 1, n))
+    return out
 
 
 def synthetic_source(arr, G, n_reg):
@@ -244,16 +275,20 @@ def main():
         flat_path = workload_files(args.workload)
     barrier()
     flat_path = workload_files(args.workload)
-    arr = load_arrays(flat_path)
+    arr1 = load_arrays(flat_path)
+    S = int(arr1["n_seg_reference"][0])       # per plane
+    n_reg1 = int(arr1["n_reg"][0])
+    arr = stack_planes(arr1, world)            # N > 1: one stack of N planes, rank r owns plane r
     G, n_reg, n_plane = (int(arr[k][0]) for k in ("n_group", "n_reg", "n_plane"))
-    S = int(arr["n_seg_reference"][0])
-    bcpg, n_surf = int(arr["bc_per_group"][0]), int(arr["n_surf"][0])
+    bcpg, n_surf, nsp = int(arr["bc_per_group"][0]), int(arr["n_surf"][0]), int(arr["n_surf_plane"][0])
     n_inner = int(arr["n_inner"][0])
     gs = args.boundary == "gs"
     src = synthetic_source(arr, G, n_reg)
+    own = [rank] if world > 1 else list(range(n_plane))  # macroplanes of this rank's handle
 
     sw = Sweeper(arr, device=local, boundary_update=0 if gs else 1, kernel=args.kernel, max_polar=args.max_polar,
-                 cache_groups=args.cache_groups)
+                 cache_groups=args.cache_groups, plane_begin=rank if world > 1 else 0,
+                 plane_end=rank + 1 if world > 1 else 0)
     # a dedicated non-default stream: the C ABI treats a NULL stream as "use the handle's own", and
     # torch events only see work on the stream they are recorded on
     stream = torch.cuda.Stream()
@@ -263,7 +298,7 @@ def main():
     sw.set_source(0, src)
     sw.set_flux(0, np.ones((G, n_reg)))
     bc0 = np.full((G, bcpg), 1.0 / (4.0 * np.pi))
-    for ip in range(n_plane):
+    for ip in own:
         sw.set_boundary(ip, 0, bc0)
 
     def step_device():
@@ -280,23 +315,45 @@ def main():
         return t.numpy()
     src = pinned(src)
     flux_h = pinned(np.ones((G, n_reg)))
-    bc_h = [pinned(bc0) for _ in range(n_plane)]
+    bc_h = {ip: pinned(bc0) for ip in own}
     h2d = d2h = 0
+    # N > 1: exchange buffers of the per-sweep all-gather (device) and where every rank keeps the whole picture (host)
+    n_pack = sw.pack_results_device(0) if world > 1 else 0
+    n_pack_max = n_reg1 + 2 * (nsp + int(arr["n_cell_plane"][0]))  # the last plane also carries the top faces
+    send = torch.zeros(n_pack_max, dtype=torch.float64, device="cuda") if world > 1 else None
+    recv = torch.zeros(world * n_pack_max, dtype=torch.float64, device="cuda") if world > 1 else None
+    recv_h = torch.empty(world * n_pack_max, dtype=torch.float64, pin_memory=True) if world > 1 else None
+    comm_events = []
 
-    def step_e2e(count=False):
+    def step_e2e(count=False, time_comm=False):
         nonlocal h2d, d2h
         groups = [range(G)] if args.mode == "batched" else [[g] for g in range(G)]
+        blist = [bc_h[ip] if ip in bc_h else None for ip in range(n_plane)]
         for gl in groups:
             # what the C++ plugin does around every sweep(group): one fused upload (source, flux, incoming
-            # boundary flux), the sweep, one fused download (flux, boundary flux, coarse tallies)
+            # boundary flux of the handle's planes), the sweep, one fused download
             for g in gl:
-                sw.set_sweep_inputs(g, src[g], flux_h[g], [bc_h[ip][g] for ip in range(n_plane)])
+                sw.set_sweep_inputs(g, src[g], flux_h[g], [b[g] if b is not None else None for b in blist])
             sw.sweep(gl[0], len(gl), n_inner=n_inner, tally_mode=TALLY_CURRENT)
             for g in gl:
-                sw.get_sweep_results(g, flux_h[g], [bc_h[ip][g] for ip in range(n_plane)], coarse=True)
-        if count:
-            h2d = G * 8 * (2 * n_reg + n_plane * bcpg)
-            d2h = G * 8 * (n_reg + n_plane * bcpg + 2 * n_surf)
+                if world == 1:
+                    sw.get_sweep_results(g, flux_h[g], [b[g] if b is not None else None for b in blist], coarse=True)
+                    continue
+                # N ranks: flux + coarse tallies of every plane to every rank -- packed on the device, ONE NCCL
+                # all-gather, one copy to pinned host memory; the rank's own outgoing boundary flux comes back too
+                sw.pack_results_device(g, send.data_ptr(), n_pack_max)
+                if time_comm:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                dist.all_gather_into_tensor(recv, send)
+                if time_comm:
+                    e1.record(stream)
+                    comm_events.append((e0, e1))
+                recv_h.copy_(recv, non_blocking=True)
+                sw.get_sweep_results(g, None, [b[g] if b is not None else None for b in blist], coarse=False)
+        if count:  # whole job
+            h2d = world * G * 8 * (2 * n_reg1 + len(own) * bcpg)
+            d2h = world * G * 8 * ((world * n_pack_max if world > 1 else n_reg1 + 2 * n_surf) + len(own) * bcpg)
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -337,7 +394,8 @@ def main():
     # contract figure: 6.10 B per update, reference layout, per-group sweep. The resident layout
     # shares geometry between the polar copies; its own compulsory bytes are reported beside it.
     n_useg = int(arr["seg_len"].size)
-    n_ray = int(arr["n_ray_reference"][0])
+    n_ray = int(arr1["n_ray_reference"][0])
+    n_reg = n_reg1  # the roofline terms below are per plane = per rank
     bytes_contract = BYTES_PER_UPDATE * 2.0 * S if (args.mode == "pergroup" and args.workload == "c5g7_2d") else \
         12.0 * S + groups_per_call * (24.0 * n_reg + 32.0 * n_ray)
     bytes_resident = 12.0 * n_useg + groups_per_call * (24.0 * n_reg + 32.0 * n_ray)
@@ -359,6 +417,16 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = updates_step * args.steps / float(t.item())
+    comm = None
+    if world > 1:  # device time of the all-gathers of one more step (max over ranks)
+        step_e2e(time_comm=True)
+        torch.cuda.synchronize()
+        cm = torch.tensor([sum(a.elapsed_time(b) for a, b in comm_events)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+        comm = {"collective": "ncclAllGather of [flux | coarse current | surface flux] slices, one per sweep(group)",
+                "calls_per_step": len(comm_events), "bytes_per_call_per_rank": 8 * n_pack_max,
+                "ms_per_step": float(cm.item()), "share_of_e2e_step": float(cm.item()) / (float(t.item()) / args.steps * 1e3)}
+        assert n_pack <= n_pack_max
     # the clock sampler covers the device-resident AND the end-to-end timed regions (both under load)
     clocks = sampler.stop() if sampler else None
 
@@ -378,6 +446,39 @@ def main():
                              f"last inner): {r['updates']:.3e} updates in {r['seconds']:.2f} s, reference MoCSweeper "
                              f"(OpenMP, unmodified sources in oracle/_ref)"}
 
+    # ---- the plugin inside MOCC's own eigenvalue solve of the same input (rank 0, N = 1): what CudaMoCSweeper::sweep
+    #      delivers (pageable Blitz/Eigen arrays, post_sweep on the host) and the time to converge next to the
+    #      reference sweeper on this box's host cores ----
+    plugin = None
+    solve_bin = os.path.join(BIN, "mocc_b200_solve")
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "c5g7_2d" and os.path.exists(solve_bin):
+        import re
+        import tempfile
+
+        def solve(sweeper_type):
+            with tempfile.TemporaryDirectory() as td:
+                out = subprocess.run([solve_bin, "c5g7_2d.xml", os.path.join(td, "out.arrays"), "--set",
+                                      f"solver/sweeper@type={sweeper_type}"], cwd=os.path.join(BIN, "inputs"),
+                                     env=dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1)),
+                                     capture_output=True, text=True)
+            m = re.search(r"outers=(\d+) k=([-0-9.e+]+) sweep_seconds=([0-9.e+-]+) device_sweep_ms=([0-9.e+-]+) "
+                          r"solve_seconds=([0-9.e+-]+)", out.stdout)
+            return None if not m else {"outers": int(m.group(1)), "k": float(m.group(2)), "sweep_s": float(m.group(3)),
+                                       "device_sweep_ms": float(m.group(4)), "solve_s": float(m.group(5))}
+        sw.synchronize()
+        pl, rf = solve("moc_cuda"), solve("moc")
+        if pl and rf:
+            upd = 2.0 * S * G * n_inner
+            plugin = {"e2e_plugin": {"value": upd * pl["outers"] / pl["sweep_s"], "unit": UNIT,
+                                     "what": "2 S G n_inner outers / MoC-sweeper timer of mocc_b200_solve (upload, sweeps, "
+                                             "download, moc::Current::post_sweep; pageable host arrays)",
+                                     "device_only": upd * pl["outers"] / (pl["device_sweep_ms"] * 1e-3)},
+                      "time_to_converge_s": {"plugin": pl["solve_s"], "reference": rf["solve_s"],
+                                             "reference_threads": os.cpu_count() or 1, "outers_plugin": pl["outers"],
+                                             "outers_reference": rf["outers"], "k_plugin": pl["k"], "k_reference": rf["k"],
+                                             "dk_pcm": (pl["k"] - rf["k"]) * 1e5, "sweep_s_plugin": pl["sweep_s"],
+                                             "sweep_s_reference": rf["sweep_s"]}}
+
     st = sw.stats()
     kname = {1: "item", 2: "track", 3: "cached", 4: "chunk", 5: "rchunk"}.get(int(st["kernel"]), "?")
     if args.mode == "batched" and kname in ("chunk", "rchunk"):
@@ -395,6 +496,7 @@ def main():
             "arm": {"kernel": kname, "resident_segments": n_useg, "bundled_segments": int(st["swept_segments"]),
                     "max_polar": args.max_polar or 2, "cache_groups": args.cache_groups or G},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "comm": comm,
             "gpu_launches": int(ln.item()),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -406,6 +508,7 @@ def main():
                          "resident_layout_bytes_per_launch": bytes_resident,
                          "achieved_resident_layout": bytes_resident / (sweep_ms * 1e-3) / 1e9},
             "cpu_baseline": cpu,
+            **(plugin or {}),
         }))
     sw.close()
     if world > 1:

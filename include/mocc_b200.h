@@ -20,7 +20,8 @@
  *                                                                     core/boundary_condition.cpp:145-191
  *   mocb200_get_coarse        <- moc::Current::post_ray tallies       sweepers/moc/moc_current_worker.hpp:202-264
  *   mocb200_set_sweep_inputs,
- *   mocb200_get_sweep_results <- everything MoCSweeper::sweep reads    sweepers/moc/moc_sweeper.cpp:197-219
+ *   mocb200_get_sweep_results,
+ *   mocb200_pack_results_device <- everything MoCSweeper::sweep reads    sweepers/moc/moc_sweeper.cpp:197-219
  *                                from / leaves in source_, flux_(:, g), boundary_[plane], coarse_data_
  *                                (the single-array calls above, fused: one copy each way, one synchronisation)
  *   mocb200_set_sn_xs,
@@ -228,6 +229,16 @@ int mocb200_set_sweep_inputs(mocb200_sweeper *h, int group, const double *source
                              const double *const *boundary);
 int mocb200_get_sweep_results(mocb200_sweeper *h, int group, double *flux, double *const *boundary, double *current,
                               double *surface_flux);
+
+/*
+ * Multi-rank exchange (one process per GPU, planes sharded by plane_begin/plane_end): packs this handle's part of
+ * the results of `group` into a DEVICE buffer of the caller, on the handle's stream, with no host round trip:
+ * [scalar flux of its FSR range][radial coarse current of its planes' surfaces][their surface flux]. The buffer
+ * is what the ranks exchange with one ncclAllGather per sweep(group) -- the only inter-GPU traffic of the path
+ * (replaces, across processes, what CoarseData / flux_ hold in the single-process reference: coarse_data.hpp:151-152,
+ * transport_sweeper.hpp:139-150). dst_device == NULL: *count receives the doubles the handle would write.
+ */
+int mocb200_pack_results_device(mocb200_sweeper *h, int group, double *dst_device, size_t capacity, size_t *count);
 
 /* Raw radial coarse tallies of the last TALLY_CURRENT/CORRECTIONS sweep for one group:
  * current[n_surf], surface_flux[n_surf] (whole-mesh surface indexing, x/y-normal surfaces of

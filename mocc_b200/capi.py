@@ -128,6 +128,7 @@ def load_library(path=None):
     lib.mocb200_get_corrections.argtypes = [H, C.c_int, _f64p, _f64p]
     lib.mocb200_set_sweep_inputs.argtypes = [H, C.c_int, _f64p, _f64p, C.POINTER(_f64p)]
     lib.mocb200_get_sweep_results.argtypes = [H, C.c_int, _f64p, C.POINTER(_f64p), _f64p, _f64p]
+    lib.mocb200_pack_results_device.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.mocb200_get_stats.argtypes = [H, C.POINTER(Stats)]
     lib.mocb200_last_sweep_ms.argtypes = [H, _f64p]
     lib.mocb200_set_timing.argtypes = [H, C.c_int]
@@ -292,12 +293,21 @@ class Sweeper:
                     bptr[ip] = _ptr(b)
         if flux is not None:
             assert flux.dtype == np.float64 and flux.flags.c_contiguous and flux.size == self.n_reg
-        cur = np.empty(self.n_surf) if coarse else None
-        sf = np.empty(self.n_surf) if coarse else None
+        cur = np.zeros(self.n_surf) if coarse else None  # a handle fills the surfaces of its own planes
+        sf = np.zeros(self.n_surf) if coarse else None
         self._ck(self.lib.mocb200_get_sweep_results(self.h, group, _ptr(flux) if flux is not None else None, bptr,
                                                     _ptr(cur) if coarse else None, _ptr(sf) if coarse else None),
                  "get_sweep_results")
         return cur, sf
+
+    def pack_results_device(self, group, device_ptr=None, capacity=0):
+        """Packs [flux of the handle's FSR range | coarse current | surface flux of its planes] into a device buffer
+        (raw pointer, e.g. tensor.data_ptr()) on the handle's stream; returns the doubles written (size query with
+        device_ptr None)."""
+        n = C.c_size_t()
+        self._ck(self.lib.mocb200_pack_results_device(self.h, group, C.c_void_p(device_ptr) if device_ptr else None,
+                                                      C.c_size_t(capacity), C.byref(n)), "pack_results_device")
+        return n.value
 
     def stats(self):
         s = Stats()

@@ -1971,7 +1971,8 @@ int mocb200_set_sweep_inputs(mocb200_sweeper *h, int group, const double *source
         CUDA_TRY(h, cudaEventSynchronize(h->ev_in));
         h->ev_in_pending = false;
     }
-    const size_t nr = (size_t)h->n_reg, nb = (size_t)h->bcpg;
+    // only the FSR range of this handle's macroplanes travels (the host arrays keep their global indexing)
+    const size_t nr = (size_t)(h->reg_hi - h->reg_lo), nb = (size_t)h->bcpg;
     size_t off = 0;
     bool staged = false;
     // pageable arrays are packed into the pinned staging buffer (one copy for all of them, flushed at the
@@ -1999,10 +2000,10 @@ int mocb200_set_sweep_inputs(mocb200_sweeper *h, int group, const double *source
         return MOCB200_OK;
     };
     const size_t o_src = off;
-    if (source && (rc = put(source, nr)))
+    if (source && (rc = put(source + h->reg_lo, nr)))
         return rc;
     const size_t o_flux = off;
-    if (flux && (rc = put(flux, nr)))
+    if (flux && (rc = put(flux + h->reg_lo, nr)))
         return rc;
     const size_t o_bc = off;
     std::vector<int> bc_planes;
@@ -2026,9 +2027,9 @@ int mocb200_set_sweep_inputs(mocb200_sweeper *h, int group, const double *source
         h->stats.kernel_launches++;
     };
     if (source)
-        scatter(h->d_in + o_src, h->n_reg, h->d_src);
+        scatter(h->d_in + o_src, (int64_t)nr, h->d_src + (size_t)h->reg_lo * h->GP);
     if (flux)
-        scatter(h->d_in + o_flux, h->n_reg, h->d_flux);
+        scatter(h->d_in + o_flux, (int64_t)nr, h->d_flux + (size_t)h->reg_lo * h->GP);
     for (size_t i = 0; i < bc_planes.size(); i++) {
         const size_t poff = (size_t)bc_planes[i] * h->bcpg * h->GP;
         scatter(h->d_in + o_bc + i * nb, h->bcpg, h->d_bc[0] + poff);
@@ -2048,7 +2049,10 @@ int mocb200_get_sweep_results(mocb200_sweeper *h, int group, double *flux, doubl
     if ((current == nullptr) != (surface_flux == nullptr))
         return fail(h, MOCB200_ERR_INVALID, "get_sweep_results: current and surface_flux go together");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    const size_t nr = (size_t)(h->reg_hi - h->reg_lo), nb = (size_t)h->bcpg, ns = (size_t)h->n_surf;
+    // coarse surfaces of this handle's macroplanes (the last plane's top faces ride along: never tallied radially)
+    const size_t s_lo = (size_t)h->plane_begin * h->n_surf_plane;
+    const size_t s_hi = h->plane_end == h->n_plane ? (size_t)h->n_surf : (size_t)h->plane_end * h->n_surf_plane;
+    const size_t nr = (size_t)(h->reg_hi - h->reg_lo), nb = (size_t)h->bcpg, ns = s_hi - s_lo;
     auto gather = [&](const double *src, int64_t n, double *cols) {
         gather_columns_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, h->stream>>>(n, h->GP, group, 1, src, cols);
         h->stats.kernel_launches++;
@@ -2070,8 +2074,8 @@ int mocb200_get_sweep_results(mocb200_sweeper *h, int group, double *flux, doubl
     }
     const size_t o_cur = off;
     if (current) {
-        gather(h->d_current, h->n_surf, h->d_out + off);
-        gather(h->d_surfflux, h->n_surf, h->d_out + off + ns);
+        gather(h->d_current + s_lo * h->GP, (int64_t)ns, h->d_out + off);
+        gather(h->d_surfflux + s_lo * h->GP, (int64_t)ns, h->d_out + off + ns);
         off += 2 * ns;
     }
     if (off == 0)
@@ -2089,8 +2093,8 @@ int mocb200_get_sweep_results(mocb200_sweeper *h, int group, double *flux, doubl
     for (size_t i = 0; i < bc_planes.size(); i++)
         pieces.push_back({boundary[bc_planes[i]], o_bc + i * nb, nb, is_pinned(boundary[bc_planes[i]])});
     if (current) {
-        pieces.push_back({current, o_cur, ns, is_pinned(current)});
-        pieces.push_back({surface_flux, o_cur + ns, ns, is_pinned(surface_flux)});
+        pieces.push_back({current + s_lo, o_cur, ns, is_pinned(current)});
+        pieces.push_back({surface_flux + s_lo, o_cur + ns, ns, is_pinned(surface_flux)});
     }
     bool any_staged = false;
     for (const Piece &pc : pieces) {
@@ -2105,6 +2109,33 @@ int mocb200_get_sweep_results(mocb200_sweeper *h, int group, double *flux, doubl
     for (const Piece &pc : pieces)
         if (!pc.direct)
             std::memcpy(pc.dst, h->h_out + pc.off, pc.n * sizeof(double));
+    return MOCB200_OK;
+}
+
+int mocb200_pack_results_device(mocb200_sweeper *h, int group, double *dst_device, size_t capacity, size_t *count)
+{
+    int rc = check_groups(h, group, 1);
+    if (rc)
+        return rc;
+    if (!count)
+        return fail(h, MOCB200_ERR_INVALID, "pack_results_device: count is NULL");
+    const size_t s_lo = (size_t)h->plane_begin * h->n_surf_plane;
+    const size_t s_hi = h->plane_end == h->n_plane ? (size_t)h->n_surf : (size_t)h->plane_end * h->n_surf_plane;
+    const size_t nr = (size_t)(h->reg_hi - h->reg_lo), ns = s_hi - s_lo;
+    *count = nr + 2 * ns;
+    if (!dst_device)
+        return MOCB200_OK; // size query
+    if (capacity < *count)
+        return fail(h, MOCB200_ERR_INVALID, "pack_results_device: buffer holds %zu doubles, %zu needed", capacity, *count);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    auto gather = [&](const double *src, int64_t n, double *cols) {
+        gather_columns_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, h->stream>>>(n, h->GP, group, 1, src, cols);
+        h->stats.kernel_launches++;
+    };
+    gather(h->d_flux + (size_t)h->reg_lo * h->GP, (int64_t)nr, dst_device);
+    gather(h->d_current + s_lo * h->GP, (int64_t)ns, dst_device + nr);
+    gather(h->d_surfflux + s_lo * h->GP, (int64_t)ns, dst_device + nr + ns);
+    CUDA_TRY(h, cudaGetLastError());
     return MOCB200_OK;
 }
 

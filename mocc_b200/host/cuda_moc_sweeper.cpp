@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <exception>
 #include <sstream>
+#include <thread>
 
 #include "core/coarse_data.hpp"
 #include "core/source.hpp"
@@ -111,6 +113,8 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
             throw EXCEPT(msg.str());
         }
         parts_.push_back(part);
+        part_ms_.push_back(0.0);
+        mocb200_set_timing(part.h, 1); // CUDA events around the sweep kernels of every inner (device_sweep_ms)
         mocb200_get_stats(part.h, &stats_);
         LogFile << "B200 MoC sweeper: device " << part.device << " owns macroplanes [" << part.plane_begin << ", "
                 << part.plane_end << "): " << stats_.segments_per_sweep << " segments per sweep, "
@@ -154,6 +158,32 @@ CudaMoCSweeper::~CudaMoCSweeper()
             mocb200_destroy(p.h);
 }
 
+// fn(part) for every device part; with several parts one host thread each, so that the blocking
+// device->host copies (and the packing into pinned staging) of the devices overlap. The C ABI is
+// thread-compatible per handle: every call sets its own device.
+template <class Fn> void CudaMoCSweeper::for_each_part(Fn &&fn)
+{
+    if (parts_.size() == 1) {
+        fn(parts_[0], 0);
+        return;
+    }
+    std::vector<std::exception_ptr> err(parts_.size());
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < parts_.size(); i++)
+        th.emplace_back([&, i]() {
+            try {
+                fn(parts_[i], i);
+            } catch (...) {
+                err[i] = std::current_exception();
+            }
+        });
+    for (auto &t : th)
+        t.join();
+    for (auto &e : err)
+        if (e)
+            std::rethrow_exception(e);
+}
+
 void CudaMoCSweeper::check(const Part &p, int rc, const char *what) const
 {
     if (rc != MOCB200_OK) {
@@ -180,10 +210,11 @@ void CudaMoCSweeper::upload_group(int group)
         std::copy(xstr_.xs().begin(), xstr_.xs().end(), col_.begin());
     const VectorX &src = source_->get();
     if (send_xs)
-        for (const Part &p : parts_)
+        for_each_part([&](const Part &p, size_t) {
             check(p, mocb200_set_xs(p.h, group, 1, col_.data(), &xstr_true_fsr_[(size_t)group * n_reg_],
                                     &xs_self_fsr_[(size_t)group * n_reg_]),
                   "mocb200_set_xs");
+        });
     xs_uploaded_[group] = true;
     for (int ireg = 0; ireg < (int)n_reg_; ireg++)
         col_[ireg] = flux_(ireg, group);
@@ -191,17 +222,19 @@ void CudaMoCSweeper::upload_group(int group)
     std::vector<const double *> bc(n_macroplane_, nullptr);
     for (int ip = 0; ip < n_macroplane_; ip++)
         bc[ip] = boundary_[ip].get_boundary(group, 0).second;
-    for (const Part &p : parts_)
+    for_each_part([&](const Part &p, size_t) {
         check(p, mocb200_set_sweep_inputs(p.h, group, src.data(), col_.data(), bc.data()), "mocb200_set_sweep_inputs");
+    });
 }
 
 void CudaMoCSweeper::download_flux(int group)
 {
-    for (const Part &p : parts_) {
-        check(p, mocb200_get_flux(p.h, group, 1, col_.data()), "mocb200_get_flux");
+    // every handle writes the FSR range of its own macroplanes (the rest of col_ is left alone)
+    for_each_part([&](const Part &p, size_t) {
+        check(p, mocb200_get_sweep_results(p.h, group, col_.data(), nullptr, nullptr, nullptr), "mocb200_get_sweep_results");
         for (int ireg = p.reg_lo; ireg < p.reg_hi; ireg++)
             flux_(ireg, group) = col_[ireg];
-    }
+    });
 }
 
 // Device results of one group -> host objects the rest of MOCC reads.
@@ -214,9 +247,16 @@ void CudaMoCSweeper::download_group(int group, int tally)
     const bool coarse = tally != MOCB200_TALLY_NONE;
     if (coarse)
         coarse_data_->zero_data_radial(group); // moc_sweeper.cpp:208-215: zero the radial data, tally, flag
-    for (const Part &p : parts_) {
-        check(p, mocb200_get_sweep_results(p.h, group, col_.data(), bc.data(), coarse ? cur_.data() : nullptr,
-                                           coarse ? sflux_.data() : nullptr),
+    // the devices are drained concurrently (one host thread per handle): flux and boundary flux land in
+    // disjoint ranges of the host arrays, the coarse tallies in per-device buffers
+    const size_t n_surf = mesh_.n_surf();
+    if (coarse && cur_.size() < parts_.size() * n_surf) {
+        cur_.resize(parts_.size() * n_surf);
+        sflux_.resize(parts_.size() * n_surf);
+    }
+    for_each_part([&](const Part &p, size_t i) {
+        double *cur = cur_.data() + i * n_surf, *sfl = sflux_.data() + i * n_surf;
+        check(p, mocb200_get_sweep_results(p.h, group, col_.data(), bc.data(), coarse ? cur : nullptr, coarse ? sfl : nullptr),
               "mocb200_get_sweep_results");
         for (int ireg = p.reg_lo; ireg < p.reg_hi; ireg++)
             flux_(ireg, group) = col_[ireg];
@@ -225,12 +265,18 @@ void CudaMoCSweeper::download_group(int group, int tally)
             // division by the surface area, moc_current_worker.hpp:272-318) so every quirk is kept
             for (int ip = p.plane_begin; ip < p.plane_end; ip++) {
                 for (int s = mesh_.plane_surf_xy_begin(ip); s < (int)mesh_.plane_surf_end(ip); s++) {
-                    coarse_data_->current(s, group)      = cur_[s];
-                    coarse_data_->surface_flux(s, group) = sflux_[s];
+                    coarse_data_->current(s, group)      = cur[s];
+                    coarse_data_->surface_flux(s, group) = sfl[s];
                 }
             }
         }
-    }
+        // device time of this sweep(group): CUDA events around the sweep kernels of every inner (the handles
+        // run concurrently: the slowest one counts)
+        double ms = 0.0;
+        int64_t n  = 0;
+        if (mocb200_get_timing(p.h, &ms, &n) == MOCB200_OK)
+            part_ms_[i] += ms;
+    });
     if (coarse) {
         moc::Current cw(coarse_data_, &mesh_);
         cw.set_group(group);
@@ -286,13 +332,7 @@ void CudaMoCSweeper::sweep(int group)
         for (int ig = g0; ig < g0 + gc; ig++)
             download_group(ig, tally);
         t_download_ += since(t2);
-        double ms_max = 0.0;
-        for (const Part &p : parts_) {
-            double ms = 0.0;
-            if (mocb200_last_sweep_ms(p.h, &ms) == MOCB200_OK)
-                ms_max = std::max(ms_max, ms);
-        }
-        device_sweep_ms_ += ms_max * n_inner_; // last inner timed; inners are alike; slowest GPU counts
+        device_sweep_ms_ = *std::max_element(part_ms_.begin(), part_ms_.end()); // slowest GPU
     };
     if (!group_batch_)
         run(group, 1);
@@ -356,8 +396,7 @@ void CudaMoCSweeper2D3D::before_last_inner(int group)
     for (int ip = 0; ip < n_macroplane_; ip++)
         for (int ic = 0; ic < ncp; ic++)
             sn_col_[(size_t)ip * ncp + ic] = xstr_sn_[ic + plane_xs_offset_[ip]];
-    for (const Part &p : parts_)
-        check(p, mocb200_set_sn_xs(p.h, group, 1, sn_col_.data()), "mocb200_set_sn_xs");
+    for_each_part([&](const Part &p, size_t) { check(p, mocb200_set_sn_xs(p.h, group, 1, sn_col_.data()), "mocb200_set_sn_xs"); });
 }
 
 // Device correction factors -> CorrectionData, with the residual bookkeeping of
@@ -366,8 +405,9 @@ void CudaMoCSweeper2D3D::post_group(int group, int tally)
 {
     if (tally != MOCB200_TALLY_CORRECTIONS)
         return;
-    for (const Part &p : parts_) // each handle fills the cells of its own macroplanes
+    for_each_part([&](const Part &p, size_t) { // each handle fills the cells of its own macroplanes
         check(p, mocb200_get_corrections(p.h, group, alpha_.data(), beta_.data()), "mocb200_get_corrections");
+    });
     const int ncp       = mesh_.nx() * mesh_.ny();
     const size_t n_cell = (size_t)n_macroplane_ * ncp;
     const int n_ang     = ang_quad_.ndir() / 4; // sweep angles (octants 1-2)

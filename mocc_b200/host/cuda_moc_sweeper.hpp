@@ -78,6 +78,7 @@ protected:
         int device = 0, plane_begin = 0, plane_end = 0, reg_lo = 0, reg_hi = 0;
     };
     void check(const Part &p, int rc, const char *what) const;
+    template <class Fn> void for_each_part(Fn &&fn); // fn(part, index), one host thread per part
     void upload_group(int group);
     void download_group(int group, int tally);
 
@@ -92,6 +93,7 @@ protected:
     std::vector<int> plane_xs_offset_; // CurrentCorrections::mplane_offset_
     std::vector<double> col_, cur_, sflux_;
     double device_sweep_ms_ = 0.0;
+    std::vector<double> part_ms_; // per device: sum over all sweep(group) calls of the event time of every inner
     // wall-clock split of sweep(): host->device, host work between the inners (2D3D), waiting for the
     // device + device->host, host post-processing; reported at destruction
     double t_upload_ = 0.0, t_host_mid_ = 0.0, t_download_ = 0.0, t_enqueue_ = 0.0;

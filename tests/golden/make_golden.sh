@@ -67,3 +67,19 @@ save_arrays(sys.argv[2], {"k_history": a["k_history"], "flux_sample": np.asconti
                           "flux_sum": np.array([flux.sum()]), "pin_powers": a["pin_powers"]})
 PY
 )
+
+# C5G7 3-D (BASELINE.json config 4) with the settings under which the reference's own 2D3D iteration settles
+# (profiles/r2/c5g7_3d.md): transverse-leakage splitting on the MoC side, 10 Sn inners, one host thread.
+#   c5g7_3d_12_ref : the full problem (3 x 3 assemblies of 17 x 17 pins, 9 planes), 12 outers: k stationary to
+#                    +-3 pcm from outer 8 on (the reference's iteration breaks down at outer 14)
+#   c5g7_3d_n9_ref : the same problem with every assembly cut to its central 9 x 9 pins, 24 outers: k stationary
+#                    to +-1.5 pcm from outer 9 on
+# Compact goldens (tools/pack_solve_golden.py): k history, every 97th flux entry, flux sum, pin powers.
+for v in "12:--max-iter 12" "n9:--lattice-n 9 --max-iter 24"; do
+    name="c5g7_3d_${v%%:*}"
+    python "$ROOT/tools/make_c5g7_3d.py" "$ROOT/mocc_b200/bin/inputs/c5g7_2d.xml" "$WORK/$name.xml" ${v#*:} \
+        --sn-inner 10 --moc-attrs 'tl_splitting="t"'
+    (cd "$WORK" && OMP_NUM_THREADS=1 "$SOLVE" $name.xml "$WORK/$name.arrays" > "$WORK/$name.solve.log" 2>&1) \
+        || { tail -5 "$WORK/$name.solve.log"; exit 1; }
+    python "$ROOT/tools/pack_solve_golden.py" "$WORK/$name.arrays" "$HERE/${name}_ref.arrays.gz"
+done

@@ -58,3 +58,34 @@ def test_two_ranks_gather_plane_slices(tmp_path):
         full = np.load(tmp_path / f"full_{r}.npy")
         assert not np.isnan(full).any()
         assert np.array_equal(full, rec["flux_out"])  # the oracle is bit-identical to the reference record
+
+
+def test_stacked_planes_sweep_like_the_single_plane():
+    """bench.py --gpus N sweeps ONE stack of N copies of the workload's plane (rank r owns plane r): the stacked
+    problem must be a valid multi-plane problem whose planes behave exactly like the original one. Checked with
+    the CPU oracle: every plane of the 3-plane stack reproduces the single-plane sweep bit for bit (flux, boundary
+    flux, coarse tallies at the plane's own surface range)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle_lib import oracle_sweep1g
+    flat, gold = load_case("mini2d_gs")
+    rec = records(gold)[1]
+    mode = int(rec["mode"][0])
+    f1, bc1, cur1, sf1 = oracle_sweep1g(flat, rec["xstr"], rec["qbar"], rec["bc_in"], gs_boundary=True, tally_mode=mode)
+    n = 3
+    st = bench.stack_planes({k: v for k, v in flat.items()} | {"xs_tr": np.zeros((1, int(flat["n_reg"][0]))),
+                                                               "xs_self": np.zeros((1, int(flat["n_reg"][0]))),
+                                                               "xs_nf": np.zeros((1, int(flat["n_reg"][0]))),
+                                                               "xs_ch": np.zeros((1, int(flat["n_reg"][0]))),
+                                                               "xs_scat": np.zeros((1, 1, int(flat["n_reg"][0])))}, n)
+    R, nsp = int(flat["n_reg"][0]), int(flat["n_surf_plane"][0])
+    assert int(st["n_reg"][0]) == n * R and int(st["n_surf"][0]) == n * nsp + int(flat["n_cell_plane"][0])
+    fN, bcN, curN, sfN = oracle_sweep1g(st, np.tile(rec["xstr"], n), np.tile(rec["qbar"], n),
+                                        np.tile(rec["bc_in"].reshape(1, -1), (n, 1)), gs_boundary=True, tally_mode=mode)
+    nxy = int(flat["nx"][0]) * int(flat["ny"][0])
+    for ip in range(n):
+        assert np.array_equal(fN[ip * R:(ip + 1) * R], f1)
+        assert np.array_equal(bcN[ip], bc1[0])
+        if mode == 1:  # radial surfaces of the plane (the first nx*ny of every plane's range are its bottom faces)
+            assert np.array_equal(curN[ip * nsp + nxy:(ip + 1) * nsp], cur1[nxy:nsp])
+            assert np.array_equal(sfN[ip * nsp + nxy:(ip + 1) * nsp], sf1[nxy:nsp])
