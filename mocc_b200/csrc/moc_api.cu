@@ -837,8 +837,11 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                 const int nreg_pl = (ip + 1 < p.n_plane ? p.plane_first_reg[ip + 1] : p.n_reg) - p.plane_first_reg[ip];
                 rc_plane_start[ip + 1] = rc_plane_start[ip] + ((nreg_pl + 3) & ~3);
                 const int u = p.plane_unique[ip];
-                if (ip < h->plane_begin || ip >= h->plane_end)
+                if (ip < h->plane_begin || ip >= h->plane_end) { // not swept by this handle: any one-to-one placement
+                    for (int r = 0; r < nreg_pl; r++)
+                        perm[(size_t)p.plane_first_reg[ip] + r] = rc_plane_start[ip] + r;
                     continue;
+                }
                 if (rc_lperm[u].empty()) {
                     static const char *no_group = getenv("MOCB200_RC_NOGROUP"); // tuning hook: keep the reference numbering
                     if (no_group && no_group[0] == '1') {
@@ -2160,7 +2163,7 @@ int mocb200_set_sn_xs(mocb200_sweeper *h, int g_begin, int g_count, const double
     if (!xs)
         return fail(h, MOCB200_ERR_INVALID, "set_sn_xs: NULL array");
     if (!h->have_corr)
-        return fail(h, MOCB200_ERR_STATE, "problem was created without the 2D3D correction tables");
+        return fail(h, MOCB200_ERR_STATE, "2D3D correction factors unavailable: %s", h->corr_why.c_str());
     CUDA_TRY(h, cudaSetDevice(h->device));
     if ((rc = upload_columns(h, xs, (int64_t)h->n_plane * h->n_cell_plane, g_begin, g_count, h->d_sn_xs)))
         return rc;

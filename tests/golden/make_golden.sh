@@ -72,10 +72,10 @@ PY
 # (profiles/r2/c5g7_3d.md): transverse-leakage splitting on the MoC side, 10 Sn inners, one host thread.
 #   c5g7_3d_12_ref : the full problem (3 x 3 assemblies of 17 x 17 pins, 9 planes), 12 outers: k stationary to
 #                    +-3 pcm from outer 8 on (the reference's iteration breaks down at outer 14)
-#   c5g7_3d_n9_ref : the same problem with every assembly cut to its central 9 x 9 pins, 24 outers: k stationary
+#   c5g7_3d_n9_ref : the same problem with every assembly cut to its central 9 x 9 pins (ray spacing 0.045), 24 outers: k stationary
 #                    to +-1.5 pcm from outer 9 on
 # Compact goldens (tools/pack_solve_golden.py): k history, every 97th flux entry, flux sum, pin powers.
-for v in "12:--max-iter 12" "n9:--lattice-n 9 --max-iter 24"; do
+for v in "12:--max-iter 12" "n9:--lattice-n 9 --spacing 0.045 --max-iter 24"; do
     name="c5g7_3d_${v%%:*}"
     python "$ROOT/tools/make_c5g7_3d.py" "$ROOT/mocc_b200/bin/inputs/c5g7_2d.xml" "$WORK/$name.xml" ${v#*:} \
         --sn-inner 10 --moc-attrs 'tl_splitting="t"'
