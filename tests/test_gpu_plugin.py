@@ -176,7 +176,7 @@ def _devices(which):
 def test_c5g7_3d_subproblem_settled_k_matches_reference(tmp_path, devices):
     """C5G7-class 3-D problem (3 x 3 assemblies cut to 9 x 9 pins, 6 fuel + 3 reflector planes, vacuum top / east /
     south) solved with the 2D3D method, transverse-leakage splitting ON (the tl_splitting upload path), 24 outers:
-    the reference's k settles to +-1.5 pcm from outer 9 on (0.99250); the plugin follows the reference's whole k
+    the reference's k settles to +-2.5 pcm from outer 9 on (0.99251); the plugin follows the reference's whole k
     history to 1e-7 (bar: 1 pcm = 1e-5) and its flux to 1e-5 (entries of at least 1 % of the largest flux; see the
     full-size test for the tail)."""
     # ray spacing 0.045: at 0.05 a few rays of this geometry pass exactly through pin-cell corners, which the per-FSR
@@ -185,7 +185,7 @@ def test_c5g7_3d_subproblem_settled_k_matches_reference(tmp_path, devices):
     ref = _golden("c5g7_3d_n9_ref.arrays.gz")
     rel = _check_compact(res, ref, k_tol=1e-7, flux_tol=1e-5, tiny_flux=0.01)
     k = res["k_history"]
-    assert np.max(np.abs(k[8:] - k[-1])) < 3e-5  # settled
+    assert np.max(np.abs(k[8:] - k[-1])) < 5e-5  # settled: +-2.5 pcm around 0.99251
     print(f"c5g7_3d n9: k {k[-1]:.10f} (ref {ref['k_history'][-1]:.10f}) flux rel {rel:.2e} sweep_seconds "
           f"{res['sweep_seconds'][0]:.2f} solve_seconds {res['solve_seconds'][0]:.2f} devices {devices}")
 

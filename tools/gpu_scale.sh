@@ -16,6 +16,8 @@ for n in (1, 2, 4, 8):
     except Exception as e:
         continue
     base = base or d["value"]
-    print(f"N={n} value {d['value']:.4g} e2e {d['e2e']['value']:.4g} ms/step {d['ms_per_step']:.3f} x{d['value']/base:.2f}")
+    base_e = locals().get("base_e") or d["e2e"]["value"]
+    comm = d.get("comm") or {}
+    print(f"N={n} value {d['value']:.4g} x{d['value']/base:.2f} e2e {d['e2e']['value']:.4g} x{d['e2e']['value']/base_e:.2f} "
+          f"ms/step {d['ms_per_step']:.3f} comm ms/step {comm.get('ms_per_step', 0):.3f}")
 PY
-timeout 600 python -m pytest tests/test_gpu_plugin.py -m gpu -q -k "sharded" 2>&1 | tail -2
