@@ -22,7 +22,8 @@ geometry, the plane sharding the 2D3D method uses); rank r creates its handle wi
 plane_end = r + 1. Planes are independent inside a sweep (no collective in `value`); the e2e leg adds what
 the host solver needs after every sweep(group): the ranks' flux and coarse current / surface-flux slices,
 packed on the device (mocb200_pack_results_device) and exchanged with ONE NCCL all-gather per sweep(group),
-then copied to every rank's pinned host memory; `comm` reports the device time of those all-gathers
+then copied to pinned host memory (everything on rank 0, where a single-process host solver would run; the own
+planes on the other ranks); `comm` reports the device time of those all-gathers
 (scaling "weak": one plane per GPU).
 
 --impl reference times the UNMODIFIED reference CPU sweeper (oracle/_ref/ref_tool, OpenMP on
@@ -349,11 +350,16 @@ def main():
                 if time_comm:
                     e1.record(stream)
                     comm_events.append((e0, e1))
-                recv_h.copy_(recv, non_blocking=True)
+                # the whole picture goes to the host where the (single-process) host solver runs: rank 0; the other
+                # ranks keep host mirrors of their own planes only
+                if rank == 0:
+                    recv_h.copy_(recv, non_blocking=True)
+                else:
+                    recv_h[:n_pack_max].copy_(send, non_blocking=True)
                 sw.get_sweep_results(g, None, [b[g] if b is not None else None for b in blist], coarse=False)
         if count:  # whole job
             h2d = world * G * 8 * (2 * n_reg1 + len(own) * bcpg)
-            d2h = world * G * 8 * ((world * n_pack_max if world > 1 else n_reg1 + 2 * n_surf) + len(own) * bcpg)
+            d2h = G * 8 * (((2 * world - 1) * n_pack_max if world > 1 else n_reg1 + 2 * n_surf) + world * len(own) * bcpg)
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 

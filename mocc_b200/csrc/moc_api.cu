@@ -1371,6 +1371,24 @@ int check_groups(mocb200_sweeper *h, int g_begin, int g_count)
     return MOCB200_OK;
 }
 
+// host columns [g_count][n_total], rows [r0, r1) of every column -> device [n_total][GP]: what a handle that owns
+// a plane range needs of a per-FSR array
+int upload_column_rows(mocb200_sweeper *h, const double *host, int64_t n_total, int64_t r0, int64_t r1, int g_begin,
+                       int g_count, double *dst)
+{
+    const int64_t nr = r1 - r0;
+    for (int g = 0; g < g_count; g++)
+        std::memcpy(h->h_stage + (size_t)g * nr, host + (size_t)g * n_total + r0, (size_t)nr * sizeof(double));
+    const size_t elems = (size_t)nr * g_count;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, h->h_stage, elems * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    scatter_columns_kernel<<<grid_for((int64_t)elems, 256, h->sm_count), 256, 0, h->stream>>>(nr, h->GP, g_begin, g_count,
+                                                                                             h->d_stage, dst + (size_t)r0 * h->GP);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream)); // the pinned staging buffer is reused by the next call
+    return MOCB200_OK;
+}
+
 // host columns [g_count][n] -> device [n][GP]
 int upload_columns(mocb200_sweeper *h, const double *host, int64_t n, int g_begin, int g_count, double *dst)
 {
@@ -1571,11 +1589,12 @@ int mocb200_set_xs(mocb200_sweeper *h, int g_begin, int g_count, const double *x
     if (!xstr || !xs_self)
         return fail(h, MOCB200_ERR_INVALID, "xstr and xs_self are required");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    if ((rc = upload_columns(h, xstr, h->n_reg, g_begin, g_count, h->d_xstr)))
+    // only the FSR range of this handle's macroplanes (the host arrays keep their global indexing)
+    if ((rc = upload_column_rows(h, xstr, h->n_reg, h->reg_lo, h->reg_hi, g_begin, g_count, h->d_xstr)))
         return rc;
-    if ((rc = upload_columns(h, xstr_src ? xstr_src : xstr, h->n_reg, g_begin, g_count, h->d_xstr_src)))
+    if ((rc = upload_column_rows(h, xstr_src ? xstr_src : xstr, h->n_reg, h->reg_lo, h->reg_hi, g_begin, g_count, h->d_xstr_src)))
         return rc;
-    if ((rc = upload_columns(h, xs_self, h->n_reg, g_begin, g_count, h->d_xs_self)))
+    if ((rc = upload_column_rows(h, xs_self, h->n_reg, h->reg_lo, h->reg_hi, g_begin, g_count, h->d_xs_self)))
         return rc;
     for (int g = g_begin; g < g_begin + g_count; g++) {
         h->have_xs[g]     = true;

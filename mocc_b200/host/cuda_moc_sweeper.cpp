@@ -411,10 +411,13 @@ void CudaMoCSweeper2D3D::post_group(int group, int tally)
     const int ncp       = mesh_.nx() * mesh_.ny();
     const size_t n_cell = (size_t)n_macroplane_ * ncp;
     const int n_ang     = ang_quad_.ndir() / 4; // sweep angles (octants 1-2)
-    std::array<real_t, 3> resid = {{0.0, 0.0, 0.0}};
+    // one pass over (plane, angle, cell): 4.7 M entries per group on C5G7-3D, spread over the host threads (with one
+    // thread the residual sums run in the reference's plane / angle / cell order)
+    real_t r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma omp parallel for collapse(2) reduction(+ : r0, r1, r2) schedule(static)
     for (int ip = 0; ip < n_macroplane_; ip++) {
-        const int cell_offset = mesh_.coarse_cell_offset(ip);
         for (int a = 0; a < n_ang; a++) {
+            const int cell_offset = mesh_.coarse_cell_offset(ip);
             for (int ic = 0; ic < ncp; ic++) {
                 const int icc = ic + cell_offset;
                 for (int iang : {a, (int)ang_quad_.reverse(a)}) {
@@ -422,11 +425,11 @@ void CudaMoCSweeper2D3D::post_group(int group, int tally)
                     const real_t ay = alpha_[((size_t)iang * n_cell + icc) * 2 + 1];
                     const real_t b  = beta_[(size_t)iang * n_cell + icc];
                     real_t e        = ax - corrections_->alpha(icc, iang, group, Normal::X_NORM);
-                    resid[0] += e * e;
+                    r0 += e * e;
                     e = ay - corrections_->alpha(icc, iang, group, Normal::Y_NORM);
-                    resid[1] += e * e;
+                    r1 += e * e;
                     e = b - corrections_->beta(icc, iang, group);
-                    resid[2] += e * e;
+                    r2 += e * e;
                     corrections_->alpha(icc, iang, group, Normal::X_NORM) = ax;
                     corrections_->alpha(icc, iang, group, Normal::Y_NORM) = ay;
                     corrections_->beta(icc, iang, group)                  = b;
@@ -434,6 +437,7 @@ void CudaMoCSweeper2D3D::post_group(int group, int tally)
             }
         }
     }
+    std::array<real_t, 3> resid = {{r0, r1, r2}};
     correction_residuals_[group].push_back({{std::sqrt(resid[0]), std::sqrt(resid[1]), std::sqrt(resid[2])}});
 }
 
