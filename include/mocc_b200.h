@@ -60,8 +60,7 @@ extern "C" {
 
 /* exponential evaluation */
 #define MOCB200_EXP_TABLE 0    /* Exponential_Linear<N> table in shared memory, bit-identical entries */
-#define MOCB200_EXP_FACTORED 1 /* same grid + linear interpolation, grid values from two bank-replicated
-                                  factor tables (<= 2 ulp from the table entries) */
+#define MOCB200_EXP_FACTORED 1 /* reserved (not implemented: mocb200_create rejects it) */
 
 /* sweep kernel selection (diagnostics / A-B measurements) */
 #define MOCB200_KERNEL_AUTO 0   /* RCHUNK when the attenuation cache fits in device memory, else TRACK */

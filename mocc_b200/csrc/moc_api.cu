@@ -572,6 +572,8 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
         h->plane_end = p.n_plane;
     if (h->plane_begin < 0 || h->plane_end > p.n_plane || h->plane_begin >= h->plane_end)
         return fail(h, MOCB200_ERR_INVALID, "bad plane range [%d, %d)", h->plane_begin, h->plane_end);
+    if (opt.exp_mode != MOCB200_EXP_TABLE)
+        return fail(h, MOCB200_ERR_INVALID, "exp_mode %d is not implemented (only MOCB200_EXP_TABLE)", opt.exp_mode);
     int max_polar = opt.max_polar <= 0 ? 2 : std::min<int>(opt.max_polar, kMaxPolar);
 
     // FSR range of this handle's planes (planes are stored contiguously, ascending)
@@ -1665,6 +1667,8 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         return rc;
     if (n_inner < 1)
         return fail(h, MOCB200_ERR_INVALID, "n_inner must be >= 1");
+    if (use_qbar && n_inner > 1)
+        return fail(h, MOCB200_ERR_INVALID, "use_qbar sweeps the q-bar of mocb200_set_qbar as it is: n_inner must be 1");
     if (tally_mode < MOCB200_TALLY_NONE || tally_mode > MOCB200_TALLY_CORRECTIONS)
         return fail(h, MOCB200_ERR_INVALID, "unknown tally mode %d", tally_mode);
     if (tally_mode == MOCB200_TALLY_CORRECTIONS) {

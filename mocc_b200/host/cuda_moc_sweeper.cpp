@@ -390,7 +390,7 @@ void CudaMoCSweeper2D3D::sweep(int group)
 void CudaMoCSweeper2D3D::before_last_inner(int group)
 {
     if (group == 0 || !group_batch_)
-        parallel_update(*sn_xs_mesh_); // = sn_xs_mesh_->update(), pins spread over the host threads
+        xs_updater_.update(*sn_xs_mesh_); // = sn_xs_mesh_->update(), pins spread over the host threads
     xstr_sn_.expand(group);
     const int ncp = mesh_.nx() * mesh_.ny();
     for (int ip = 0; ip < n_macroplane_; ip++)

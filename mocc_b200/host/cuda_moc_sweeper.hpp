@@ -31,6 +31,7 @@
 #include "sweepers/cmdo/correction_data.hpp"
 
 #include "mocc_b200.h"
+#include "xs_updater.hpp"
 
 namespace mocc_b200 {
 
@@ -101,9 +102,6 @@ protected:
     mocb200_stats stats_{};
 };
 
-// XSMeshHomogenized::update() with the pin loop spread over the host threads (xs_update_parallel.cpp)
-void parallel_update(mocc::XSMeshHomogenized &xs);
-
 // The per-plane MoC sweeper of the 2D3D method on the B200: same interface as
 // cmdo::MoCSweeper_2D3D (src/sweepers/cmdo/moc_sweeper_2d3d.hpp:25-88), so that the reference's
 // PlaneSweeper_2D3D can hold it in place of the CPU class (plane_sweeper_2d3d_cuda.cpp).
@@ -135,6 +133,7 @@ protected:
 private:
     std::shared_ptr<mocc::CorrectionData> corrections_;
     std::shared_ptr<mocc::XSMeshHomogenized> sn_xs_mesh_;
+    XsUpdater xs_updater_;
     mocc::ExpandedXS xstr_sn_;
     bool internal_coupling_ = false;
     std::vector<double> sn_col_, alpha_, beta_;

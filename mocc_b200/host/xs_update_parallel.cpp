@@ -26,6 +26,7 @@
 #include <string>
 #include <vector>
 
+// std headers are all included above: lifting the access specifiers only touches the reference header itself
 #define private public
 #define protected public
 #include "core/xs_mesh_homogenized.hpp"
@@ -34,6 +35,8 @@
 
 #include "core/core_mesh.hpp"
 #include "util/error.hpp"
+
+#include "xs_updater.hpp"
 
 using namespace mocc;
 
@@ -166,12 +169,23 @@ bool same_bits(const XSMeshRegion &a, const XSMeshRegion &b, int ng)
 
 } // namespace
 
-void parallel_update(XSMeshHomogenized &xs)
+// The flattened tables live as long as the sweeper that owns the updater (which also holds the shared_ptr to the
+// mesh they describe): no process-wide state, nothing keyed on an address that could be reused.
+struct XsUpdaterImpl {
+    Homogenizer hom;
+};
+
+XsUpdater::XsUpdater() : impl_(new XsUpdaterImpl())
+{
+}
+XsUpdater::~XsUpdater() = default;
+
+void XsUpdater::update(XSMeshHomogenized &xs)
 {
     if (!xs.flux_)
         return; // volume-weighted cross sections: nothing to update (xs_mesh_homogenized.cpp:178-181)
     assert(xs.flux_->extent(0) == (int)xs.mesh_.n_reg(MeshTreatment::PLANE));
-    static Homogenizer hom;
+    Homogenizer &hom = impl_->hom;
     if (hom.owner != &xs) {
         hom = Homogenizer();
         hom.build(xs);
