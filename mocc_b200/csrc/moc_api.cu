@@ -146,7 +146,13 @@ struct mocb200_sweeper {
     bool ev_valid = false;
     bool timing   = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<int> ev_inners; // inner sweeps an event pair brackets (persistent launches: several)
     size_t ev_used = 0;
+    // persistent register-chunk sweep (all plain inners of a call in one cooperative launch)
+    int rc_interleave = 1; // MOCB200_RC_INTERLEAVE=0|1 (A/B hook)
+    int persist_mode = 0; // 0: one launch per boundary phase; 1: persistent; 2: + requests in front of the grid barriers
+    unsigned int *d_gridbar = nullptr;
+    bool persist_attr_set[5] = {false, false, false, false, false};
     // stats
     mocb200_stats stats{};
     std::string error;
@@ -244,6 +250,7 @@ void build_crossings(const mocb200_problem &p, int64_t t, int nseg, std::vector<
 
 // ---- register-chunk kernel: launch geometry and batch packing ----
 RcFn pick_rc_kernel(int np, int tally, const RcConfig &c); // below
+RcPersistFn pick_rc_persist_kernel(int np, const RcConfig &c);
 
 constexpr int kRcSmemBudget = 232448 - 4096; // opt-in dynamic shared memory per CTA minus the static part
 
@@ -981,6 +988,18 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                                        (size_t)h->track_grid * 8 * h->rc_scratch_per_team);
         if ((rc2 = dev_alloc(h, &h->d_scratch, n_sc)))
             return rc2;
+        if ((rc2 = dev_alloc(h, &h->d_gridbar, (size_t)4)))
+            return rc2;
+        {
+            // default: persistent with prefetch; MOCB200_RC_PERSIST=0|1|2 (A/B hook). Needs every CTA of the grid
+            // resident at once (cooperative launch), which one CTA per SM always is.
+            const char *pm  = getenv("MOCB200_RC_PERSIST");
+            int coop        = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+            h->persist_mode = coop ? (pm ? std::max(0, std::min(2, atoi(pm))) : 2) : 0;
+            const char *il   = getenv("MOCB200_RC_INTERLEAVE");
+            h->rc_interleave = il ? atoi(il) : 1;
+        }
     }
 
     // ---- 2D3D correction-factor tables ----
@@ -1262,6 +1281,16 @@ typedef void (*RcCacheFn)(const RcCacheArgs);
 // the instantiations live in moc_rc_p{1,2,4}.cu (one translation unit per lane count, compiled in parallel)
 // the tallying sweeps need more registers per thread: one team less per CTA when that instantiation exists
 RcConfig rc_tally_config(int np, int tally, const RcConfig &c);
+
+RcPersistFn pick_rc_persist_kernel(int np, const RcConfig &c)
+{
+    switch (np) {
+    case 1: return pick_rc_persist_kernel_p1(c);
+    case 2: return pick_rc_persist_kernel_p2(c);
+    case 4: return pick_rc_persist_kernel_p4(c);
+    }
+    return nullptr;
+}
 
 RcFn pick_rc_kernel(int np, int tally, const RcConfig &c)
 {
@@ -1786,7 +1815,103 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         }
     }
 
-    for (int inner = 0; inner < n_inner; inner++) {
+    // ---- persistent path: every plain inner of this call in one cooperative launch (moc_rchunk_kernel.cuh) ----
+    int inner0 = 0;
+    if (rchunk && !use_qbar && h->n_counters <= 256 && h->persist_mode > 0) {
+        const TrackList *pl[2] = {nullptr, nullptr};
+        int n_in_phase[2]      = {0, 0};
+        for (const auto &tl : h->tlists)
+            if (tl.phase == 0 || tl.phase == 1)
+                pl[tl.phase] = &tl, n_in_phase[tl.phase]++;
+        const int n_phases = jacobi ? 1 : 2;
+        bool ok            = n_in_phase[0] == 1 && n_in_phase[1] == (jacobi ? 0 : 1);
+        if (ok && !jacobi)
+            ok = pl[0]->rc.P == pl[1]->rc.P && pl[0]->rc.LMAX == pl[1]->rc.LMAX && pl[0]->rc.NW == pl[1]->rc.NW &&
+                 pl[0]->rc.TEAMS == pl[1]->rc.TEAMS;
+        const int m = tally_mode != MOCB200_TALLY_NONE ? n_inner - 1 : n_inner;
+        RcPersistFn pfn = nullptr;
+        if (ok && m >= 1)
+            pfn = pick_rc_persist_kernel(pl[0]->rc.P, RcConfig{pl[0]->rc.LMAX, pl[0]->rc.NW, pl[0]->rc.TEAMS});
+        if (pfn) {
+            const RcList &rc0 = pl[0]->rc;
+            const size_t dsm  = (size_t)rc0.TEAMS * rc_team_bytes(rc0.P, rc0.LMAX, rc0.NW);
+            if (!h->persist_attr_set[rc0.P]) {
+                CUDA_TRY(h, cudaFuncSetAttribute((const void *)pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                h->persist_attr_set[rc0.P] = true;
+            }
+            const int ss_grid = grid_for((int64_t)h->n_reg * g_count, 256, h->sm_count);
+            self_scatter_q_kernel<<<ss_grid, 256, 0, h->stream>>>(
+                h->n_reg, h->GP, g_begin, g_count, h->d_src, h->d_flux, h->d_xs_self, h->d_xstr_src, h->d_xstr, h->d_qbar,
+                h->d_qg, nullptr, h->d_tg, 1, 1, h->d_counters, h->n_counters, h->d_fsr_perm, h->n_regp);
+            h->stats.kernel_launches++;
+            CUDA_TRY(h, cudaMemsetAsync(h->d_gridbar, 0, sizeof(unsigned int), h->stream));
+            RcPersistArgs pa{};
+            int64_t max_items = 0;
+            for (int ph = 0; ph < n_phases; ph++) {
+                const TrackList &tl = *pl[ph];
+                const RcList &rc    = tl.rc;
+                RcArgs &c           = pa.ph[ph];
+                c.units = rc.d_units, c.n_units = rc.n_units, c.pinfo = rc.d_pinfo, c.n_planes = tl.n_planes;
+                c.plane_first_reg = h->d_plane_first_reg, c.seg_fsr = h->d_pseg_fsr, c.n_regp = h->n_regp;
+                c.chunk_trk = rc.d_chunk_trk;
+                c.tracks = tl.d_cunits, c.batch_hdr = rc.d_batch_hdr, c.cache = tl.d_cache, c.n_slots = rc.n_slots;
+                c.cache_groups = h->cache_slots, c.cache_g0 = sliding ? g_begin : 0;
+                c.wt_v_st = h->d_wt, c.n_ang = h->n_ang, c.bc_per_group = h->bcpg;
+                c.g_begin = g_begin, c.g_count = g_count, c.GP = h->GP, c.n_reg = h->n_reg;
+                c.q = h->d_qg, c.tally = h->d_tg;
+                c.scratch = h->d_scratch, c.scratch_per_team = h->rc_scratch_per_team;
+                c.interleave = h->rc_interleave;
+                max_items = std::max(max_items, (int64_t)rc.n_units * tl.n_planes * g_count);
+            }
+            pa.n_phases = n_phases, pa.n_inner = m, pa.finalize_last = m < n_inner ? 1 : 0;
+            pa.prefetch = h->persist_mode - 1;
+            pa.bc[0] = h->d_bc[h->bc_cur], pa.bc[1] = jacobi ? h->d_bc[1 - h->bc_cur] : h->d_bc[h->bc_cur];
+            RcFinalizeArgs &f = pa.fin;
+            f.n_reg = h->n_reg, f.GP = h->GP, f.g_begin = g_begin, f.g_count = g_count, f.reg_lo = h->reg_lo;
+            f.reg_hi = h->reg_hi, f.n_regp = h->n_regp, f.tally = h->d_tg, f.xstr = h->d_xstr, f.vol = h->d_vol;
+            f.qbar = h->d_qbar, f.flux = h->d_flux, f.src = h->d_src, f.xs_self = h->d_xs_self;
+            f.xstr_src = h->d_xstr_src, f.q_out = h->d_qg, f.perm = h->d_fsr_perm;
+            pa.barrier = h->d_gridbar;
+            const int pgrid =
+                (int)std::max<int64_t>(1, std::min<int64_t>((max_items + rc0.TEAMS - 1) / rc0.TEAMS, h->sm_count));
+            const bool whole = m == n_inner;
+            if (whole)
+                CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+            if (h->timing) {
+                if (h->ev_used == h->ev_pool.size()) {
+                    cudaEvent_t a = nullptr, b = nullptr;
+                    CUDA_TRY(h, cudaEventCreate(&a));
+                    CUDA_TRY(h, cudaEventCreate(&b));
+                    h->ev_pool.emplace_back(a, b);
+                    h->ev_inners.push_back(1);
+                }
+                h->ev_inners[h->ev_used] = m;
+                CUDA_TRY(h, cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream));
+            }
+            void *kargs[] = {(void *)&pa};
+            CUDA_TRY(h, cudaLaunchCooperativeKernel((const void *)pfn, dim3(pgrid), dim3(32 * rc0.NW * rc0.TEAMS), kargs, dsm,
+                                                    h->stream));
+            h->stats.kernel_launches++;
+            h->stats.sweep_launches++;
+            if (h->timing)
+                CUDA_TRY(h, cudaEventRecord(h->ev_pool[h->ev_used++].second, h->stream));
+            if (jacobi && (m & 1))
+                h->bc_cur = 1 - h->bc_cur;
+            if (whole) {
+                CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+                h->ev_valid = true;
+                finalize_flux_q_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
+                    h->n_reg, h->GP, g_begin, g_count, h->d_tg, h->d_xstr, h->d_vol, h->d_qbar, h->d_flux, h->reg_lo,
+                    h->reg_hi, 1, h->d_fsr_perm, h->n_regp);
+                h->stats.kernel_launches++;
+                CUDA_TRY(h, cudaGetLastError());
+                return MOCB200_OK;
+            }
+            inner0 = m;
+        }
+    }
+
+    for (int inner = inner0; inner < n_inner; inner++) {
         const bool last = inner == n_inner - 1;
         const int tally = last ? tally_mode : MOCB200_TALLY_NONE;
         if (tally == MOCB200_TALLY_CORRECTIONS) {
@@ -1827,7 +1952,9 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                 CUDA_TRY(h, cudaEventCreate(&a));
                 CUDA_TRY(h, cudaEventCreate(&b));
                 h->ev_pool.emplace_back(a, b);
+                h->ev_inners.push_back(1);
             }
+            h->ev_inners[h->ev_used] = 1;
             CUDA_TRY(h, cudaEventRecord(h->ev_pool[h->ev_used].first, h->stream));
         }
         const double *bc_in = h->d_bc[h->bc_cur];
@@ -1905,6 +2032,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
                     c.g_begin = g_begin, c.g_count = g_count, c.GP = h->GP, c.n_reg = h->n_reg;
                     c.q = h->d_qg, c.tally = h->d_tg, c.bc_in = bc_in, c.bc_out = bc_out;
                     c.scratch = h->d_scratch, c.scratch_per_team = h->rc_scratch_per_team;
+                    c.interleave = h->rc_interleave;
                     c.cross = h->d_xcross, c.cur_w = h->d_curw, c.flx_w = h->d_flxw;
                     c.plane_surf_offset = h->d_plane_surf_offset, c.current = h->d_current, c.surface_flux = h->d_surfflux;
                     c.dsum = h->d_dsum, c.ssum = h->d_ssum, c.n_surf_plane = h->n_surf_plane, c.n_plane_total = h->n_plane;
@@ -2267,8 +2395,11 @@ int mocb200_get_timing(mocb200_sweeper *h, double *sweep_ms, int64_t *inner_swee
         CUDA_TRY(h, cudaEventElapsedTime(&f, h->ev_pool[i].first, h->ev_pool[i].second));
         tot += f;
     }
+    int64_t inners = 0; // an event pair of the persistent path brackets several inners
+    for (size_t i = 0; i < h->ev_used; i++)
+        inners += h->ev_inners[i];
     *sweep_ms     = tot;
-    *inner_sweeps = (int64_t)h->ev_used;
+    *inner_sweeps = inners;
     h->ev_used    = 0;
     return MOCB200_OK;
 }

@@ -98,6 +98,7 @@ struct RcArgs {
     double *tally;   // same layout
     const double *bc_in;
     double *bc_out;
+    int32_t interleave; // team numbering: 1: team * CTAs + CTA, 0: CTA * TEAMS + team
     double *scratch; // per team: backward flux entering each sub-block of a chained track, [sub-block][P]
     int32_t scratch_per_team;
     // coarse-mesh tallies of the last inner (TALLY 1: moc::Current, 2: cmdo::CurrentCorrections)
@@ -118,9 +119,22 @@ typedef void (*RcFn)(const RcArgs);
 RcFn pick_rc_kernel_p1(int tally, const RcConfig &c);
 RcFn pick_rc_kernel_p2(int tally, const RcConfig &c);
 RcFn pick_rc_kernel_p4(int tally, const RcConfig &c);
+struct RcPersistArgs;
+typedef void (*RcPersistFn)(const RcPersistArgs);
+RcPersistFn pick_rc_persist_kernel_p1(const RcConfig &c);
+RcPersistFn pick_rc_persist_kernel_p2(const RcConfig &c);
+RcPersistFn pick_rc_persist_kernel_p4(const RcConfig &c);
 
-template <int P, int LMAX, int NW, int TEAMS, int TALLY>
-__global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const RcArgs a)
+// One boundary phase of one inner sweep: every team walks its share of the work items (static round-robin).
+// Called once per launch by sweep_rchunk_kernel and once per phase and inner by sweep_rchunk_persist_kernel.
+//   s_bar, s_tot: static shared memory of the kernel (mbarriers initialised by the caller; their phase parities
+//                 par_f / par_e live across calls)
+//   bc_in/bc_out: boundary flux read / written by this phase
+//   prestage:     what rc_prefetch_first has already requested for the team's first item (0: nothing,
+//                 1: header and attenuations, 2: also the q-bar gather)
+template <int P, int LMAX, int NW, int TEAMS, int TALLY, bool PREFETCH_ONLY = false>
+__device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, double (*s_tot)[NW][P][4], uint32_t &par_f,
+                                              uint32_t &par_e, const double *bc_in, double *bc_out, int prestage)
 {
     static_assert(P == 1 || P == 2 || P == 4, "one lane per polar angle: 1, 2 or 4 lanes per chunk");
     static_assert(LMAX % 2 == 1, "odd chunk length: conflict-free shared-memory strides");
@@ -129,8 +143,6 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     constexpr int NS = rc_slots(P, LMAX, NW);   // slots per batch
     constexpr int HS = rc_header_ints(P, LMAX, NW); // int32 words of a batch header
     extern __shared__ __align__(16) double s_dyn[];
-    __shared__ uint64_t s_bar[4 * TEAMS];
-    __shared__ double s_tot[TEAMS][NW][P][4]; // per warp and polar angle: forward map (A, B), backward map (A, B) of the warp's chunks
 
     const int lane = threadIdx.x & 31;
     const int wid  = threadIdx.x >> 5;
@@ -145,19 +157,13 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     int32_t *fbuf = reinterpret_cast<int32_t *>(ab + (size_t)NS * P); // three batch-header buffers (FSR ids, lane descriptors)
     uint64_t *bar = &s_bar[4 * team];                                 // [0..2] header buffers, [3] attenuations
     auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(T) : "memory"); };
-    if (loader) {
-        for (int i = 0; i < 4; i++)
-            mbar_init(bar + i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    team_sync();
-    uint32_t par_f = 0u, par_e = 0u; // mbarrier phase parities (bit i of par_f: header buffer i)
 
     const int GP            = a.GP;
     const uint32_t per_unit = (uint32_t)a.n_planes * (uint32_t)a.g_count;
     const uint32_t total    = (uint32_t)a.n_units * per_unit;
     const uint32_t n_teams  = gridDim.x * TEAMS;
-    const uint32_t team_global = blockIdx.x * TEAMS + team;
+    // consecutive work items go to different SMs: the teams that get one item more are spread over all SMs
+    const uint32_t team_global = a.interleave ? (uint32_t)team * gridDim.x + blockIdx.x : blockIdx.x * TEAMS + team;
 
     // work item -> (unit, plane of the list, group of the launch)
     struct Item {
@@ -458,12 +464,12 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     };
     auto store_exit = [&](const Item &it, int enc, double v) {
         if (enc != INT32_MIN) {
-            double *bc_out_pl = a.bc_out + (size_t)it.plane * a.bc_per_group * GP + (a.g_begin + it.grel);
+            double *bc_out_pl = bc_out + (size_t)it.plane * a.bc_per_group * GP + (a.g_begin + it.grel);
             bc_out_pl[(size_t)(enc >= 0 ? enc : -(enc + 1)) * GP] = enc >= 0 ? v : 0.0;
         }
     };
     auto load_in = [&](const Item &it, int slot) {
-        return a.bc_in[((size_t)it.plane * a.bc_per_group + slot) * GP + (a.g_begin + it.grel)];
+        return bc_in[((size_t)it.plane * a.bc_per_group + slot) * GP + (a.g_begin + it.grel)];
     };
     // lane descriptor of a staged header (its bulk copy has been waited for by gather_q) and the two values it
     // points to: angle weight, incoming boundary flux (never written by this launch: one boundary phase)
@@ -481,17 +487,37 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
     // on their way); if the next item is a single batch too, its header has been requested into buffer (fi + 1) % 3.
     uint32_t w_cur = team_global;
     if (w_cur >= total)
-        return;
+        return 0;
     Item cur = decode(w_cur);
     uint32_t w_nxt = w_cur + n_teams;
     Item nxt{};
     if (w_nxt < total)
         nxt = decode(w_nxt);
     int fi = 0; // header buffer of `cur`
+    if constexpr (PREFETCH_ONLY) {
+        // Requests for the team's first item that do not depend on what the other CTAs are still writing: its
+        // header and attenuations (prestage 1) and, when q-bar is final already, the q-bar gather (prestage 2).
+        if (cur.nb != 1 || prestage == 0)
+            return 0;
+        team_sync(); // the team's last reduction has left the header buffers
+        issue_hdr(fi, cur.batch);
+        issue_ex(cur, cur.batch);
+        if (w_nxt < total && nxt.nb == 1)
+            issue_hdr((fi + 1) % 3, nxt.batch);
+        if (prestage == 2)
+            gather_q(fi, cur);
+        return prestage;
+    }
     int4 meta = make_int4(0, 0, INT32_MIN, 0);
     double wt = 0.0, pin = 0.0;
     bool staged = false;
     double *sc  = a.scratch + (size_t)team_global * a.scratch_per_team;
+    if (prestage != 0) { // rc_sweep_body<..., true> has requested the first item (cur.nb == 1)
+        if (prestage == 1)
+            gather_q(fi, cur);
+        lane_inputs(fi, cur, meta, wt, pin);
+        staged = true;
+    }
 
     while (true) {
         const bool have_nxt = w_nxt < total;
@@ -508,6 +534,8 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
             // ---------------- one batch: the common case ----------------
             const bool head = meta.x & kRcHead, tail = meta.x & kRcTail;
             const bool pre  = have_nxt && nxt.nb == 1;
+            // Static round-robin over equal batches. (A work counter claimed two items ahead was measured 5 % slower on
+            // C5G7-2D: the teams run at a uniform pace, there is no imbalance to win back; profiles/r2/tuning.md.)
             const uint32_t w_nn = w_nxt + n_teams;
             Item nn{};
             if (have_nxt && w_nn < total) // two items ahead: its descriptor loads fly during compose
@@ -636,6 +664,141 @@ __global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const 
                 nxt = decode(w_nxt);
             staged = false;
         }
+    }
+    return 0;
+}
+
+template <int NW, int TEAMS> __device__ __forceinline__ void rc_init_barriers(uint64_t *s_bar)
+{
+    const int wid = threadIdx.x >> 5, team = wid / NW;
+    if ((int)threadIdx.x == team * NW * 32) { // the loader lane of every team
+        for (int i = 0; i < 4; i++)
+            mbar_init(&s_bar[4 * team + i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// One boundary phase per launch (Gauss-Seidel: octants 1/3, then 2/4; Jacobi: everything).
+template <int P, int LMAX, int NW, int TEAMS, int TALLY>
+__global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_kernel(const RcArgs a)
+{
+    __shared__ uint64_t s_bar[4 * TEAMS];
+    __shared__ double s_tot[TEAMS][NW][P][4]; // per warp and polar angle: forward map (A, B), backward map (A, B) of the warp's chunks
+    rc_init_barriers<NW, TEAMS>(s_bar);
+    uint32_t par_f = 0u, par_e = 0u; // mbarrier phase parities (bit i of par_f: header buffer i)
+    rc_sweep_body<P, LMAX, NW, TEAMS, TALLY>(a, s_bar, s_tot, par_f, par_e, a.bc_in, a.bc_out, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PERSISTENT VARIANT: all plain (NoCurrent) inner iterations of one sweep(group) call in ONE cooperative launch.
+//
+// What the per-phase launches cost on C5G7-2D (profiles/r2): the two sweep kernels of an inner run 49 + 48 us, the
+// events around them measure 108.6 us (launch gaps), and inside each kernel the SMs are busy 80 % of the elapsed
+// cycles (CTA launch, a cold pipeline -- header, then the q-bar gather that needs it, then compose --, and the
+// tail). Here one CTA per SM stays resident for the whole call:
+//   for every inner: phase 0 | grid barrier | phase 1 | grid barrier | flux + next q-bar (the arithmetic of
+//   finalize_next_q_kernel, moc_sweep_kernel.cuh) | grid barrier
+// and before it arrives at a barrier every team requests what its first batch behind the barrier needs and no
+// other CTA is still writing: header + attenuations always, the q-bar gather too in front of phase 1.
+// Grid barrier: one arrival counter in global memory, release / acquire at gpu scope (the acquire also drops the
+// SM's L1 lines, which matters for q-bar and the boundary flux: both are rewritten by other SMs between phases).
+struct RcFinalizeArgs {
+    int32_t n_reg, GP, g_begin, g_count, reg_lo, reg_hi, n_regp;
+    double *tally;      // group-major [g][n_regp], regrouped numbering
+    const double *xstr; // [n_reg][GP] ...
+    const double *vol;
+    double *qbar, *flux;
+    const double *src, *xs_self, *xstr_src;
+    double *q_out; // group-major q-bar the sweep gathers from
+    const int32_t *perm;
+};
+
+struct RcPersistArgs {
+    RcArgs ph[2];       // per boundary phase (bc_in / bc_out of these are ignored)
+    int32_t n_phases;   // 2: Gauss-Seidel boundary update, 1: Jacobi
+    int32_t n_inner;    // inners swept by this launch
+    int32_t finalize_last; // 0: the last inner's flux is left to finalize_flux_q_kernel (no next q-bar)
+    int32_t prefetch;   // requests in front of the barriers: 0 none, 1 header + attenuations, 2 + q-bar gather
+    double *bc[2];      // Gauss-Seidel: bc[0] read and written; Jacobi: read bc[i & 1], write bc[1 - (i & 1)]
+    RcFinalizeArgs fin;
+    unsigned int *barrier; // zeroed by the host before the launch
+};
+
+__device__ __forceinline__ void rc_grid_sync(unsigned int *counter, unsigned int &epoch)
+{
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0) {
+        const unsigned int target = epoch * gridDim.x;
+        unsigned int seen;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        do { // relaxed polls (an acquire load would drop the L1 on every trip), one acquire fence at the end
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// flux = tally/(xstr vol) + 4 pi q-bar; q-bar' = (src + flux xs_self)/(4 pi xstr_src); tally = 0: the statements
+// of finalize_next_q_kernel (same non-contracted arithmetic), grid-strided over the CTAs of this launch.
+// with_next_q == false: the flux only (finalize_flux_q_kernel)
+__device__ __forceinline__ void rc_finalize(const RcFinalizeArgs &f, bool with_next_q)
+{
+
+    const int nr    = f.reg_hi - f.reg_lo;
+    const int64_t n = (int64_t)nr * f.g_count;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int gi    = (int)(i / nr);
+        const int r     = f.reg_lo + (int)(i - (int64_t)gi * nr);
+        const int g     = f.g_begin + gi;
+        const size_t o  = (size_t)r * f.GP + g;
+        const size_t oo = f.perm ? (size_t)gi * f.n_regp + f.perm[r] : (size_t)gi * f.n_reg + r;
+        const double t  = __ldcg(f.tally + oo);
+        const double fl = __dadd_rn(__ddiv_rn(t, __dmul_rn(f.xstr[o], f.vol[r])), __dmul_rn(f.qbar[o], kFPi));
+        f.flux[o]       = fl;
+        if (with_next_q) {
+            const double r_fpi_tr = __ddiv_rn(1.0, __dmul_rn(f.xstr_src[o], kFPi));
+            const double q        = __dmul_rn(__dadd_rn(f.src[o], __dmul_rn(fl, f.xs_self[o])), r_fpi_tr);
+            f.qbar[o]   = q;
+            f.q_out[oo] = q;
+            f.tally[oo] = 0.0;
+        }
+    }
+}
+
+template <int P, int LMAX, int NW, int TEAMS>
+__global__ void __launch_bounds__(32 * NW * TEAMS, 1) sweep_rchunk_persist_kernel(const __grid_constant__ RcPersistArgs pa)
+{
+    __shared__ uint64_t s_bar[4 * TEAMS];
+    __shared__ double s_tot[TEAMS][NW][P][4];
+    rc_init_barriers<NW, TEAMS>(s_bar);
+    uint32_t par_f = 0u, par_e = 0u;
+    unsigned int epoch = 0u;
+    const bool jacobi = pa.n_phases == 1;
+    int staged = 0; // what has been requested for the first item of the coming phase
+    for (int inner = 0; inner < pa.n_inner; inner++) {
+        const int flip       = jacobi ? (inner & 1) : 0;
+        const double *bc_in  = pa.bc[flip];
+        double *bc_out       = pa.bc[jacobi ? 1 - flip : 0];
+        staged = rc_sweep_body<P, LMAX, NW, TEAMS, 0>(pa.ph[0], s_bar, s_tot, par_f, par_e, bc_in, bc_out, staged);
+        if (!jacobi) {
+            staged = rc_sweep_body<P, LMAX, NW, TEAMS, 0, true>(pa.ph[1], s_bar, s_tot, par_f, par_e, bc_in, bc_out,
+                                                                 pa.prefetch);
+            rc_grid_sync(pa.barrier, epoch); // outgoing boundary flux of phase 0 is what phase 1 starts from
+            staged = rc_sweep_body<P, LMAX, NW, TEAMS, 0>(pa.ph[1], s_bar, s_tot, par_f, par_e, bc_in, bc_out, staged);
+        }
+        const bool more = inner + 1 < pa.n_inner;
+        if (!more && !pa.finalize_last)
+            break;
+        rc_grid_sync(pa.barrier, epoch); // every contribution to the tally has arrived
+        rc_finalize(pa.fin, true);
+        if (more) // q-bar is being rewritten: header and attenuations only
+            staged = rc_sweep_body<P, LMAX, NW, TEAMS, 0, true>(pa.ph[0], s_bar, s_tot, par_f, par_e, bc_in, bc_out,
+                                                                 pa.prefetch ? 1 : 0);
+        if (more)
+            rc_grid_sync(pa.barrier, epoch);
     }
 }
 
