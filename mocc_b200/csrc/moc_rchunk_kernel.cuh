@@ -59,11 +59,12 @@ __host__ __device__ constexpr int rc_header_ints(int P, int LMAX, int NW)
 {
     return rc_header_ints_plain(P, LMAX, NW) + 8 * rc_chunks(P, NW);
 }
-// dynamic shared memory of one team: attenuations [NS][P], q-bar [NS], contributions [NS][P] (doubles),
-// batch headers [3] (triple-buffered); tally variants keep the crossing lists in global memory
+// dynamic shared memory of one team: attenuations [NS][P], q-bar [NS], contributions [NS][P], per lane the angle
+// weight and the incoming boundary flux of the staged item (doubles), batch headers [3] (triple-buffered); tally
+// variants keep the crossing lists in global memory
 __host__ __device__ constexpr size_t rc_team_bytes(int P, int LMAX, int NW)
 {
-    return (size_t)rc_slots(P, LMAX, NW) * (size_t)(2 * P + 1) * sizeof(double) +
+    return (size_t)rc_slots(P, LMAX, NW) * (size_t)(2 * P + 1) * sizeof(double) + 2 * 32 * (size_t)NW * sizeof(double) +
            3 * (size_t)rc_header_ints(P, LMAX, NW) * sizeof(int32_t);
 }
 
@@ -154,7 +155,9 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
     double *exb   = reinterpret_cast<double *>(wbase);
     double *qb    = exb + (size_t)NS * P;
     double *ab    = qb + NS;
-    int32_t *fbuf = reinterpret_cast<int32_t *>(ab + (size_t)NS * P); // three batch-header buffers (FSR ids, lane descriptors)
+    double *s_wt  = ab + (size_t)NS * P; // per lane: angle weight, incoming boundary flux of the staged item
+    double *s_pin = s_wt + T;
+    int32_t *fbuf = reinterpret_cast<int32_t *>(s_pin + T); // three batch-header buffers (FSR ids, lane descriptors)
     uint64_t *bar = &s_bar[4 * team];                                 // [0..2] header buffers, [3] attenuations
     auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(T) : "memory"); };
 
@@ -208,7 +211,9 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
         }
     };
     constexpr int NJ = (NS + T - 1) / T;
-    auto gather_q = [&](int fi, const Item &it) { // striped: lanes on consecutive slots
+    // q-bar of the batch whose header sits in buffer fi, striped: lanes on consecutive slots. mt: the lane's
+    // descriptor from the same header (read together with the FSR ids: one shared-memory latency for all of them)
+    auto gather_q = [&](int fi, const Item &it, int4 &mt) {
         mbar_wait(bar + fi, (par_f >> fi) & 1u);
         par_f ^= 1u << fi;
         const double *qf = a.q + (size_t)it.grel * a.n_regp + it.first_reg;
@@ -218,6 +223,7 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
 #pragma unroll
         for (int j = 0; j < NJ; j++) // all shared-memory reads first: one latency, not NJ
             f[j] = (NS % T == 0 || tl + j * T < NS) ? fb[tl + j * T] : 0;
+        mt = *reinterpret_cast<const int4 *>(fb + NS + 4 * tl);
 #pragma unroll
         for (int j = 0; j < NJ; j++)
             if (NS % T == 0 || tl + j * T < NS)
@@ -229,6 +235,21 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
         par_e ^= 1u;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         team_sync();
+    };
+    // Angle weight and incoming boundary flux of the lane for a staged item: asynchronous 8-byte copies into the
+    // team's shared memory, complete with the q-bar gather (wait_staged), read by take_inputs. (Loading them into
+    // registers one item ahead made the consumer wait for the NEXT item's loads as well: the loop's loads share a
+    // scoreboard -- 11 % of the stall samples, profiles/r2/tuning.md.) The boundary values read here are never
+    // written by the same phase.
+    auto stage_inputs = [&](const Item &it, const int4 &mt) {
+        cp_async_8(s_wt + tl, a.wt_v_st + it.plane * a.n_ang + (mt.x >> 8));
+        if (mt.x & (kRcHead | kRcTail))
+            cp_async_8(s_pin + tl, bc_in + ((size_t)it.plane * a.bc_per_group + mt.y) * GP + (a.g_begin + it.grel));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto take_inputs = [&](const int4 &mt, double &wt_o, double &pin_o) { // behind wait_staged
+        wt_o  = s_wt[tl];
+        pin_o = (mt.x & (kRcHead | kRcTail)) ? s_pin[tl] : 0.0;
     };
     auto reduce_tally = [&](int fi, const Item &it) { // striped again: one red per slot
         double *tf = a.tally + (size_t)it.grel * a.n_regp + it.first_reg;
@@ -255,9 +276,12 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
             }
         }
 #pragma unroll
-        for (int j = 0; j < NJ; j++)
-            if (f[j] >= 0) // explicit state space: a generic atomicAdd on the laundered pointer would be an ATOM with a result
-                asm volatile("red.global.add.f64 [%0], %1;" ::"l"(tf + (uint32_t)f[j]), "d"(v[j]) : "memory");
+        for (int j = 0; j < NJ; j++) // predicated, explicit state space (a generic atomicAdd on the laundered pointer
+                                     // would be an ATOM with a result; an `if` around it costs a branch per slot)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 0;\n\t@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(
+                             tf + (uint32_t)(f[j] & 0x7fffffff)),
+                         "d"(v[j]), "r"(f[j])
+                         : "memory");
     };
 
     // ---- the lane's chunk: load once, keep 1 - e and q-bar in registers ----
@@ -283,7 +307,12 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
     // Scan over the chunks of the team. In: the forward / backward map of the lane's chunk (with the resets of
     // track heads / tails folded in). Out: the flux entering the chunk in both directions (valid for chunks that
     // are not heads / tails themselves); team_total: the team's total maps (chained tracks).
-    auto scan = [&](const Maps &m, double &psi_f, double &psi_b, Maps *team_total) {
+    // Two halves around ONE team barrier (the caller's: it also frees the staging buffers): scan_warp -- butterfly
+    // over the lanes of the warp, the warp's total maps to shared memory; scan_team -- the other warps' totals.
+    struct ScanState {
+        double EfA, EfB, EbA, EbB, TAf, TF, TAb, TB;
+    };
+    auto scan_warp = [&](const Maps &m, ScanState &st) {
         double EfA = 1.0, EfB = 0.0, EbA = 1.0, EbB = 0.0;
         double TAf = m.Af, TF = m.Bf, TAb = m.Ab, TB = m.Bb;
 #pragma unroll
@@ -307,13 +336,17 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
             TAf *= oAf;
             TAb *= oAb;
         }
+        if (NW > 1 && lane < P) { // every lane of polar angle p holds the warp's total maps
+            s_tot[team][wl][p][0] = TAf, s_tot[team][wl][p][1] = TF;
+            s_tot[team][wl][p][2] = TAb, s_tot[team][wl][p][3] = TB;
+        }
+        st = ScanState{EfA, EfB, EbA, EbB, TAf, TF, TAb, TB};
+    };
+    auto scan_team = [&](const ScanState &st, double &psi_f, double &psi_b, Maps *team_total) {
+        const double EfA = st.EfA, EfB = st.EfB, EbA = st.EbA, EbB = st.EbB;
+        const double TAf = st.TAf, TF = st.TF, TAb = st.TAb, TB = st.TB;
         double cf = 0.0, cb = 0.0; // flux leaving the lower / higher warps (the first chunk of a batch is a head)
         if (NW > 1) {
-            if (lane < P) { // every lane of polar angle p holds the warp's total maps
-                s_tot[team][wl][p][0] = TAf, s_tot[team][wl][p][1] = TF;
-                s_tot[team][wl][p][2] = TAb, s_tot[team][wl][p][3] = TB;
-            }
-            team_sync();
 #pragma unroll
             for (int w = 0; w < NW - 1; w++)
                 if (w < wl)
@@ -471,15 +504,6 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
     auto load_in = [&](const Item &it, int slot) {
         return bc_in[((size_t)it.plane * a.bc_per_group + slot) * GP + (a.g_begin + it.grel)];
     };
-    // lane descriptor of a staged header (its bulk copy has been waited for by gather_q) and the two values it
-    // points to: angle weight, incoming boundary flux (never written by this launch: one boundary phase)
-    auto lane_inputs = [&](int fi, const Item &it, int4 &mt, double &wt_o, double &pin_o) {
-        mt    = *reinterpret_cast<const int4 *>(fbuf + fi * HS + NS + 4 * tl);
-        wt_o  = __ldg(a.wt_v_st + it.plane * a.n_ang + (mt.x >> 8));
-        pin_o = 0.0;
-        if (mt.x & (kRcHead | kRcTail))
-            pin_o = load_in(it, mt.y);
-    };
 
     // ================= pipeline over the work items of this team (static round-robin) =================
     // Invariant at the top of a single-batch item `cur` with `staged`: its header is in buffer fi, its attenuations
@@ -504,8 +528,10 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
         issue_ex(cur, cur.batch);
         if (w_nxt < total && nxt.nb == 1)
             issue_hdr((fi + 1) % 3, nxt.batch);
-        if (prestage == 2)
-            gather_q(fi, cur);
+        if (prestage == 2) {
+            int4 mt;
+            gather_q(fi, cur, mt);
+        }
         return prestage;
     }
     int4 meta = make_int4(0, 0, INT32_MIN, 0);
@@ -514,8 +540,10 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
     double *sc  = a.scratch + (size_t)team_global * a.scratch_per_team;
     if (prestage != 0) { // rc_sweep_body<..., true> has requested the first item (cur.nb == 1)
         if (prestage == 1)
-            gather_q(fi, cur);
-        lane_inputs(fi, cur, meta, wt, pin);
+            gather_q(fi, cur, meta);
+        else
+            meta = *reinterpret_cast<const int4 *>(fbuf + fi * HS + NS + 4 * tl);
+        stage_inputs(cur, meta);
         staged = true;
     }
 
@@ -526,8 +554,8 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
             issue_ex(cur, cur.batch);
             if (have_nxt && nxt.nb == 1)
                 issue_hdr((fi + 1) % 3, nxt.batch);
-            gather_q(fi, cur);
-            lane_inputs(fi, cur, meta, wt, pin);
+            gather_q(fi, cur, meta);
+            stage_inputs(cur, meta);
             staged = true;
         }
         if (cur.nb == 1) {
@@ -541,26 +569,28 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
             if (have_nxt && w_nn < total) // two items ahead: its descriptor loads fly during compose
                 nn = decode(w_nn);
             wait_staged();
+            take_inputs(meta, wt, pin);
             double ome[LMAX], qv[LMAX];
             Maps m = compose(ome, qv);
-            team_sync(); // attenuation and q-bar buffers are free; everybody has left the previous reduction
-            // the next item: attenuations, q-bar, angle weight and incoming flux (its header was requested one item
-            // earlier); the item after it: header
-            int4 meta_n = make_int4(0, 0, INT32_MIN, 0);
-            double wt_n = 0.0, pin_n = 0.0;
-            if (pre) {
-                issue_ex(nxt, nxt.batch);
-                if (w_nn < total && nn.nb == 1)
-                    issue_hdr((fi + 2) % 3, nn.batch);
-                gather_q((fi + 1) % 3, nxt);
-                lane_inputs((fi + 1) % 3, nxt, meta_n, wt_n, pin_n);
-            }
             if (head)
                 m.Bf = fma(m.Af, pin, m.Bf), m.Af = 0.0;
             if (tail)
                 m.Bb = fma(m.Ab, pin, m.Bb), m.Ab = 0.0;
+            ScanState st;
+            scan_warp(m, st);
+            team_sync(); // the warps' totals are visible; attenuation, q-bar and input buffers are free
+            // the next item: attenuations, q-bar, angle weight and incoming flux (its header was requested one item
+            // earlier); the item after it: header
+            int4 meta_n = make_int4(0, 0, INT32_MIN, 0);
+            if (pre) {
+                issue_ex(nxt, nxt.batch);
+                if (w_nn < total && nn.nb == 1)
+                    issue_hdr((fi + 2) % 3, nn.batch);
+                gather_q((fi + 1) % 3, nxt, meta_n);
+                stage_inputs(nxt, meta_n);
+            }
             double psi_f, psi_b;
-            scan(m, psi_f, psi_b, nullptr);
+            scan_team(st, psi_f, psi_b, nullptr);
             if (head)
                 psi_f = pin;
             if (tail)
@@ -579,7 +609,7 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
                 break;
             if (pre) {
                 fi = (fi + 1) % 3;
-                meta = meta_n, wt = wt_n, pin = pin_n;
+                meta = meta_n;
             } else {
                 staged = false;
                 team_sync(); // what follows reuses the buffers at once
@@ -595,8 +625,7 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
                 team_sync(); // the previous block's reduction has left the buffers
                 issue_hdr(fi, cur.batch + b);
                 issue_ex(cur, cur.batch + b);
-                gather_q(fi, cur);
-                mt = *reinterpret_cast<const int4 *>(fbuf + fi * HS + NS + 4 * tl);
+                gather_q(fi, cur, mt);
                 wait_staged();
             };
             // pass A, highest sub-block first: the backward flux entering sub-block b - 1 from above
@@ -612,7 +641,10 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
                     m.Bb = fma(m.Ab, sc[b * P + p], m.Bb), m.Ab = 0.0;
                 double pf, pb;
                 Maps tot;
-                scan(m, pf, pb, &tot);
+                ScanState st;
+                scan_warp(m, st);
+                team_sync();
+                scan_team(st, pf, pb, &tot);
                 if (tl < P) // the total backward map has A = 0 (a tail was folded in): B is the flux leaving below
                     sc[(b - 1) * P + p] = tot.Bb;
             }
@@ -638,7 +670,10 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
                     m.Bb = fma(m.Ab, pin_b, m.Bb), m.Ab = 0.0;
                 double psi_f, psi_b;
                 Maps tot;
-                scan(m, psi_f, psi_b, &tot);
+                ScanState st;
+                scan_warp(m, st);
+                team_sync();
+                scan_team(st, psi_f, psi_b, &tot);
                 if (start_f)
                     psi_f = pin_f;
                 if (start_b)
