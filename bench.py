@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--boundary", default="gs", choices=["gs", "jacobi"])
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--persistent", type=int, default=0,
+                    help="RCHUNK kernel: 1/2 = all plain inners of a sweep call in one cooperative launch (mocb200_options)")
     ap.add_argument("--workload", default="c5g7_2d", choices=sorted(WORKLOADS))
     ap.add_argument("--max-polar", type=int, default=0, help="polar angles bundled per track (0 = library default, 2)")
     ap.add_argument("--cache-groups", type=int, default=0,
@@ -288,7 +290,7 @@ def main():
     own = [rank] if world > 1 else list(range(n_plane))  # macroplanes of this rank's handle
 
     sw = Sweeper(arr, device=local, boundary_update=0 if gs else 1, kernel=args.kernel, max_polar=args.max_polar,
-                 cache_groups=args.cache_groups, plane_begin=rank if world > 1 else 0,
+                 cache_groups=args.cache_groups, persistent=args.persistent, plane_begin=rank if world > 1 else 0,
                  plane_end=rank + 1 if world > 1 else 0)
     # a dedicated non-default stream: the C ABI treats a NULL stream as "use the handle's own", and
     # torch events only see work on the stream they are recorded on

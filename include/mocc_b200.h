@@ -169,7 +169,12 @@ typedef struct mocb200_options {
                                 super-block chaining of long tracks; negative = that cap with two-warp teams */
     int32_t cache_groups;    /* energy groups the attenuation cache holds at once: 0 = all if they fit in device memory,
                                 else as many as fit (>= 1; rebuilt per sweep call, 2 small launches per group); test hook */
-    int32_t reserved[6];
+    int32_t persistent;      /* RCHUNK kernel: 0 = one launch per boundary phase and inner (default); 1 = all plain inners
+                                of a mocb200_sweep call in ONE cooperative launch (grid barriers between the phases,
+                                flux / q-bar update inside); 2 = 1 + the first batch behind every barrier requested in
+                                front of it. Same results; needs one track list per phase (2-D problems, 3-D problems with
+                                one unique plane), otherwise ignored. Environment MOCB200_RC_PERSIST overrides (A/B hook) */
+    int32_t reserved[5];
 } mocb200_options;
 
 /* Build the device-resident problem. The host arrays may be freed afterwards. */

@@ -58,7 +58,8 @@ class Problem(C.Structure):
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("boundary_update", C.c_int32), ("exp_mode", C.c_int32),
                 ("max_polar", C.c_int32), ("block_threads", C.c_int32), ("plane_begin", C.c_int32),
-                ("plane_end", C.c_int32), ("kernel", C.c_int32), ("chunk_cap", C.c_int32), ("cache_groups", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("plane_end", C.c_int32), ("kernel", C.c_int32), ("chunk_cap", C.c_int32), ("cache_groups", C.c_int32), ("persistent", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
 
 
 class Stats(C.Structure):
@@ -154,7 +155,8 @@ class Sweeper:
     """Handle on a device-resident MoC problem (one GPU)."""
 
     def __init__(self, arrays, device=0, boundary_update=BOUNDARY_GS, exp_mode=EXP_TABLE, max_polar=0,
-                 block_threads=0, plane_begin=0, plane_end=0, kernel=0, chunk_cap=0, cache_groups=0, lib=None):
+                 block_threads=0, plane_begin=0, plane_end=0, kernel=0, chunk_cap=0, cache_groups=0, persistent=0,
+                 lib=None):
         self.lib = lib or load_library()
         self.arrays = arrays
         self.problem, self._keep = problem_from_arrays(arrays)
@@ -170,6 +172,7 @@ class Sweeper:
         opt.kernel = kernel
         opt.chunk_cap = chunk_cap
         opt.cache_groups = cache_groups
+        opt.persistent = persistent
         self.h = C.c_void_p()
         rc = self.lib.mocb200_create(C.byref(self.problem), C.byref(opt), C.byref(self.h))
         if rc != 0:

@@ -252,7 +252,7 @@ void build_crossings(const mocb200_problem &p, int64_t t, int nseg, std::vector<
 RcFn pick_rc_kernel(int np, int tally, const RcConfig &c); // below
 RcPersistFn pick_rc_persist_kernel(int np, const RcConfig &c);
 
-constexpr int kRcSmemBudget = 232448 - 4096; // opt-in dynamic shared memory per CTA minus the static part
+constexpr int kRcSmemBudget = 232448 - 1280; // opt-in shared memory per CTA minus the kernels' static part (<= 1152 B)
 
 bool rc_config_fits(int np, const RcConfig &c)
 {
@@ -991,12 +991,13 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
         if ((rc2 = dev_alloc(h, &h->d_gridbar, (size_t)4)))
             return rc2;
         {
-            // default: persistent with prefetch; MOCB200_RC_PERSIST=0|1|2 (A/B hook). Needs every CTA of the grid
+            // mocb200_options.persistent, MOCB200_RC_PERSIST=0|1|2 overrides (A/B hook). Needs every CTA of the grid
             // resident at once (cooperative launch), which one CTA per SM always is.
             const char *pm  = getenv("MOCB200_RC_PERSIST");
             int coop        = 0;
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
-            h->persist_mode = coop ? (pm ? std::max(0, std::min(2, atoi(pm))) : 2) : 0;
+            const int want  = pm ? atoi(pm) : opt.persistent;
+            h->persist_mode = coop ? std::max(0, std::min(2, want)) : 0;
             const char *il   = getenv("MOCB200_RC_INTERLEAVE");
             h->rc_interleave = il ? atoi(il) : 1;
         }

@@ -447,6 +447,49 @@ def test_two_groups_per_call_on_the_chunk_kernel(case, n_inner, kernel):
         _close(x, y, atol=1e-13)
 
 
+@pytest.mark.parametrize("persistent", [1, 2])
+@pytest.mark.parametrize("jacobi", [False, True])
+@pytest.mark.parametrize("n_inner,tally", [(1, 0), (3, 0), (4, 1)])
+@pytest.mark.parametrize("case", ["mini2d_gs", "3x3_s05_gs"])
+def test_persistent_launch_equals_per_phase_launches(case, persistent, jacobi, n_inner, tally):
+    """mocb200_options.persistent: every plain inner of a sweep call in one cooperative launch (grid barriers between
+    the boundary phases, flux / q-bar update inside the kernel) gives what the per-phase launches give: flux,
+    boundary flux and the coarse tallies of the last inner, Gauss-Seidel and Jacobi boundary update, one and two
+    groups per call."""
+    flat, gold = load_case(case)
+    G, n_reg = (int(flat[k][0]) for k in ("n_group", "n_reg"))
+    bcpg = int(flat["bc_per_group"][0])
+    rng = np.random.default_rng(11)
+    xstr = np.stack([gold[f"xs_tr_{g}"] for g in range(G)])
+    xself = np.stack([gold[f"xs_self_{g}"] for g in range(G)])
+    src = rng.uniform(0.05, 1.0, size=(G, n_reg))
+    flux0 = rng.uniform(0.5, 1.5, size=(G, n_reg))
+    bc = rng.uniform(0.0, 0.3, size=(G, bcpg))
+    res = []
+    for mode in (0, persistent):
+        sw = _sweeper(flat, boundary_update=1 if jacobi else 0, kernel=5, persistent=mode)
+        sw.set_xs(0, xstr, xstr_src=xstr, xs_self=xself)
+        sw.set_source(0, src)
+        sw.set_flux(0, flux0)
+        sw.set_boundary(0, 0, bc)
+        launches0 = sw.stats()["sweep_launches"]
+        sw.sweep(0, 1, n_inner=n_inner, tally_mode=tally)
+        sw.sweep(1, 2, n_inner=n_inner, tally_mode=tally)  # two groups per call
+        n_launch = sw.stats()["sweep_launches"] - launches0
+        out = [sw.get_flux(0, 3)] + [sw.get_boundary(0, g, 1)[0] for g in range(3)]
+        if tally:
+            for g in range(3):
+                out.extend(sw.get_coarse(g))
+        res.append((out, n_launch))
+        sw.close()
+    phases = 1 if jacobi else 2
+    plain = n_inner - (1 if tally else 0)
+    assert res[0][1] == 2 * phases * n_inner
+    assert res[1][1] == 2 * ((1 if plain else 0) + (phases if tally else 0)), "the persistent path was not taken"
+    for x, y in zip(res[0][0], res[1][0]):
+        _close(x, y, atol=1e-13)
+
+
 @pytest.mark.parametrize("case", ["mini2d_gs", "mini3d_gs"])
 @pytest.mark.parametrize("slots", [1, 2])
 def test_sliding_attenuation_cache_equals_full_cache(case, slots):
