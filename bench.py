@@ -232,6 +232,149 @@ def run_reference(args):
     }))
 
 
+def run_angle_sharded(args, arr, world, rank, local, barrier):
+    """N ranks on ONE plane (strong scaling): rank r sweeps its angle families with the reference's
+    Gauss-Seidel boundary order intact (a family is closed under the boundary update: no boundary flux travels); after
+    every inner sweep the per-FSR tally is summed over the ranks by ONE ncclAllReduce on the device buffer the handle
+    adopted, then every rank applies the flux update; the coarse tallies of the last inner are summed the same way."""
+    import torch
+    import torch.distributed as dist
+    from mocc_b200 import Sweeper
+    from mocc_b200.capi import BUF_CURRENT, BUF_SURFACE_FLUX, BUF_TALLY, TALLY_CURRENT, angle_families
+    from mocc_b200.sharding import partition_families
+    S = int(arr["n_seg_reference"][0])
+    G, n_reg = int(arr["n_group"][0]), int(arr["n_reg"][0])
+    bcpg, n_surf, n_inner = int(arr["bc_per_group"][0]), int(arr["n_surf"][0]), int(arr["n_inner"][0])
+    n_fam, fam = angle_families(arr)
+    ranges = partition_families(arr, fam, world)
+    if len(ranges) < world:
+        raise RuntimeError(f"{n_fam} angle families cannot be split over {world} ranks")
+    fb, fe = ranges[rank]
+    sw = Sweeper(arr, device=local, boundary_update=0, kernel=args.kernel, max_polar=args.max_polar,
+                 family_begin=fb, family_end=fe)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sw.set_stream(stream.cuda_stream)
+    src = synthetic_source(arr, G, n_reg)
+    sw.set_xs(0, arr["xs_tr"], xstr_src=arr["xs_tr"], xs_self=arr["xs_self"])
+    sw.set_source(0, src)
+    sw.set_flux(0, np.ones((G, n_reg)))
+    bc0 = np.full((G, bcpg), 1.0 / (4.0 * np.pi))
+    sw.set_boundary(0, 0, bc0)
+    bufs = {}
+    for which in (BUF_TALLY, BUF_CURRENT, BUF_SURFACE_FLUX):
+        _, n = sw.device_buffer(which)
+        bufs[which] = torch.zeros(n, dtype=torch.float64, device="cuda")
+        sw.adopt_device_buffer(which, bufs[which].data_ptr(), n)
+    stride = bufs[BUF_TALLY].numel() // G       # one group of the group-major tally
+    tally1 = bufs[BUF_TALLY][:stride]
+    comm_ev = []
+
+    def sweep_group(g, time_comm=False):
+        for inner in range(n_inner):
+            last = inner == n_inner - 1
+            sw.sweep_partial(g, 1, tally_mode=TALLY_CURRENT if last else 0)
+            if time_comm:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            dist.all_reduce(tally1)
+            if last:
+                dist.all_reduce(bufs[BUF_CURRENT])
+                dist.all_reduce(bufs[BUF_SURFACE_FLUX])
+            if time_comm:
+                e1.record(stream)
+                comm_ev.append((e0, e1))
+            sw.finalize_flux(g, 1)
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = a
+        return t.numpy()
+    src_h, flux_h, bc_h = pinned(src), pinned(np.ones((G, n_reg))), pinned(bc0)
+
+    def step_e2e():
+        for g in range(G):
+            sw.set_sweep_inputs(g, src_h[g], flux_h[g], [bc_h[g]])
+            sweep_group(g)
+            # every rank keeps flux and its own boundary flux; the coarse tallies go where the host solver runs
+            sw.get_sweep_results(g, flux_h[g], [bc_h[g]], coarse=rank == 0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(args.warmup):
+        for g in range(G):
+            sweep_group(g)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = sw.stats()["kernel_launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in ev:
+        flush.zero_()
+        barrier()  # strong scaling: every step starts together (untimed)
+        e0.record(stream)
+        for g in range(G):
+            sweep_group(g)
+        e1.record(stream)
+    barrier()
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    ln = torch.tensor([float(sw.stats()["kernel_launches"] - launches0)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    updates_step = 2.0 * S * G * n_inner       # ONE plane, whatever N
+    value = updates_step * args.steps / (ms * 1e-3)
+    # sweep kernels of this rank's families, per inner (CUDA events inside the library)
+    sw.set_timing(True)
+    for g in range(G):
+        sweep_group(g)
+    k_ms, k_n = sw.get_timing()
+    sw.set_timing(False)
+    for g in range(G):
+        sweep_group(g, time_comm=True)
+    torch.cuda.synchronize()
+    cm = torch.tensor([sum(a.elapsed_time(b) for a, b in comm_ev)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = updates_step * args.steps / float(te.item())
+    clocks = sampler.stop() if sampler else None
+    peak, peak_src = peaks()
+    sweep_ms = k_ms / max(k_n, 1)
+    bytes_contract = BYTES_PER_UPDATE * 2.0 * S / world if args.workload == "c5g7_2d" else None
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64",
+            "data": "examples/c5g7_2d.xml geometry and cross sections (flattened on the box); synthetic fixed source",
+            "config": dict(workload_config(args.workload, "pergroup", "gs", S, n_reg, G, n_inner, 1),
+                           shard=f"angle families: {n_fam} families over {world} ranks {ranges}, Gauss-Seidel boundary "
+                                 "order kept, no boundary exchange"),
+            "arm": {"kernel": "rchunk", "families": [fb, fe]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * G * 8 * (2 * n_reg + bcpg),
+                    "d2h_bytes_per_step": G * 8 * (world * (n_reg + bcpg) + 2 * n_surf)},
+            "comm": {"collective": "ncclAllReduce of the per-FSR tally after every inner sweep (+ coarse current and "
+                                   "surface flux after the last inner of a group)",
+                     "calls_per_step": G * (n_inner + 2), "bytes_per_tally_call": 8 * stride,
+                     "ms_per_step": float(cm.item()), "share_of_step": float(cm.item()) / (ms / args.steps)},
+            "gpu_launches": int(ln.item()), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": None if bytes_contract is None else bytes_contract / (sweep_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": None if bytes_contract is None else bytes_contract / (sweep_ms * 1e-3) / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "sweep_rchunk_kernel",
+                         "launch": "rank 0's sweep-kernel launches of one inner sweep (its angle families: 1/N of the "
+                                   "algorithmic bytes)", "ms_per_launch": sweep_ms},
+            "cpu_baseline": None,
+        }))
+    sw.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -244,6 +387,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--persistent", type=int, default=0,
                     help="RCHUNK kernel: 1/2 = all plain inners of a sweep call in one cooperative launch (mocb200_options)")
+    ap.add_argument("--shard", default="planes", choices=["planes", "angles"],
+                    help="N > 1: 'planes' = one N-plane stack, rank r owns plane r (weak scaling, one all-gather per "
+                         "sweep(group)); 'angles' = ONE plane, rank r sweeps its angle families, the FSR tally is "
+                         "all-reduced after every inner sweep (strong scaling)")
     ap.add_argument("--workload", default="c5g7_2d", choices=sorted(WORKLOADS))
     ap.add_argument("--max-polar", type=int, default=0, help="polar angles bundled per track (0 = library default, 2)")
     ap.add_argument("--cache-groups", type=int, default=0,
@@ -281,6 +428,8 @@ def main():
     arr1 = load_arrays(flat_path)
     S = int(arr1["n_seg_reference"][0])       # per plane
     n_reg1 = int(arr1["n_reg"][0])
+    if world > 1 and args.shard == "angles":
+        return run_angle_sharded(args, arr1, world, rank, local, barrier)
     arr = stack_planes(arr1, world)            # N > 1: one stack of N planes, rank r owns plane r
     G, n_reg, n_plane = (int(arr[k][0]) for k in ("n_group", "n_reg", "n_plane"))
     bcpg, n_surf, nsp = int(arr["bc_per_group"][0]), int(arr["n_surf"][0]), int(arr["n_surf_plane"][0])

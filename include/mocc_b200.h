@@ -174,7 +174,13 @@ typedef struct mocb200_options {
                                 flux / q-bar update inside); 2 = 1 + the first batch behind every barrier requested in
                                 front of it. Same results; needs one track list per phase (2-D problems, 3-D problems with
                                 one unique plane), otherwise ignored. Environment MOCB200_RC_PERSIST overrides (A/B hook) */
-    int32_t reserved[5];
+    int32_t family_begin;    /* this rank's ANGLE-FAMILY range [family_begin, family_end) of mocb200_angle_families();
+                                both 0 = all. A family is closed under track reversal, polar bundling and the boundary
+                                update, so a handle sweeps its families exactly as the whole sweep does; the FSR tally
+                                (and the coarse tallies) must be summed over the ranks between mocb200_sweep_partial and
+                                mocb200_finalize_flux (moc_sweeper_kernel.inc.hpp:155-173 split at the reduction) */
+    int32_t family_end;
+    int32_t reserved[3];
 } mocb200_options;
 
 /* Build the device-resident problem. The host arrays may be freed afterwards. */
@@ -280,6 +286,30 @@ int mocb200_get_stats(const mocb200_sweeper *h, mocb200_stats *out);
 /* Time (ms, CUDA events on the handle's stream) spent in transport-sweep kernels by the last
  * mocb200_sweep call; synchronises. */
 int mocb200_last_sweep_ms(mocb200_sweeper *h, double *ms);
+
+/*
+ * ANGLE-FAMILY SHARDING of one plane over ranks (single-plane 2-D cases). Replaces nothing in the
+ * reference (its sweep is one shared-memory loop over the angles, moc_sweeper_kernel.inc.hpp:59); what it splits is
+ * that loop: every rank sweeps the angles of its families, the per-FSR tally t_flux is summed over the ranks where the
+ * reference sums it over its threads (:155-163), then the flux update (:165-173) runs on every rank.
+ *   mocb200_angle_families   families of a problem (no device needed); family_of_angle: [2 n_ang] or NULL
+ *   mocb200_sweep_partial    ONE inner sweep (self scatter, sweep of the handle's angles, coarse tallies of those angles
+ *                            when tally_mode says so) that leaves the tally un-normalised
+ *   mocb200_device_buffer    device address and length (doubles) of what has to be summed over the ranks:
+ *                            MOCB200_BUF_TALLY (group-major [group - g_begin][stride], the swept groups first),
+ *                            MOCB200_BUF_CURRENT / _SURFACE_FLUX ([n_surf][8-padded groups])
+ *   mocb200_adopt_device_buffer  make the handle use caller-owned device memory for one of them (e.g. a tensor of the
+ *                            communication library: all-reduce in place, no copies); contents are carried over
+ *   mocb200_finalize_flux    flux = tally / (xstr vol) + 4 pi q-bar for the groups of the partial sweep
+ */
+#define MOCB200_BUF_TALLY 0
+#define MOCB200_BUF_CURRENT 1
+#define MOCB200_BUF_SURFACE_FLUX 2
+int mocb200_angle_families(const mocb200_problem *prob, int32_t *n_family, int32_t *family_of_angle);
+int mocb200_sweep_partial(mocb200_sweeper *h, int g_begin, int g_count, int tally_mode, int use_qbar);
+int mocb200_finalize_flux(mocb200_sweeper *h, int g_begin, int g_count);
+int mocb200_device_buffer(mocb200_sweeper *h, int which, void **ptr, int64_t *count);
+int mocb200_adopt_device_buffer(mocb200_sweeper *h, int which, void *ptr, int64_t count);
 
 /* Cumulative device time of the transport-sweep kernels. While enabled, every inner iteration
  * of mocb200_sweep is bracketed by a CUDA event pair on the handle's stream;

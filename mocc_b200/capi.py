@@ -59,7 +59,7 @@ class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("boundary_update", C.c_int32), ("exp_mode", C.c_int32),
                 ("max_polar", C.c_int32), ("block_threads", C.c_int32), ("plane_begin", C.c_int32),
                 ("plane_end", C.c_int32), ("kernel", C.c_int32), ("chunk_cap", C.c_int32), ("cache_groups", C.c_int32), ("persistent", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("family_begin", C.c_int32), ("family_end", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Stats(C.Structure):
@@ -134,6 +134,11 @@ def load_library(path=None):
     lib.mocb200_last_sweep_ms.argtypes = [H, _f64p]
     lib.mocb200_set_timing.argtypes = [H, C.c_int]
     lib.mocb200_get_timing.argtypes = [H, _f64p, C.POINTER(C.c_int64)]
+    lib.mocb200_angle_families.argtypes = [C.POINTER(Problem), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.mocb200_sweep_partial.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.mocb200_finalize_flux.argtypes = [H, C.c_int, C.c_int]
+    lib.mocb200_device_buffer.argtypes = [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.mocb200_adopt_device_buffer.argtypes = [H, C.c_int, C.c_void_p, C.c_int64]
     lib.mocb200_version.restype = C.c_char_p
     if path == LIB_PATH:
         _lib = lib
@@ -142,6 +147,22 @@ def load_library(path=None):
 
 def _ptr(a):
     return a.ctypes.data_as(_f64p)
+
+
+BUF_TALLY, BUF_CURRENT, BUF_SURFACE_FLUX = 0, 1, 2
+
+
+def angle_families(arrays, lib=None):
+    """(number of angle families, family of every boundary angle [2 n_ang]) of a flattened problem -- the units
+    a single plane is sharded by (mocb200_angle_families; needs no device)."""
+    lib = lib or load_library()
+    prob, keep = problem_from_arrays(arrays)
+    n = C.c_int32()
+    fam = np.zeros(2 * int(prob.n_ang), dtype=np.int32)
+    rc = lib.mocb200_angle_families(C.byref(prob), C.byref(n), fam.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc != 0:
+        raise RuntimeError(f"mocb200_angle_families failed ({rc})")
+    return n.value, fam
 
 
 def _host(a, shape):
@@ -156,7 +177,7 @@ class Sweeper:
 
     def __init__(self, arrays, device=0, boundary_update=BOUNDARY_GS, exp_mode=EXP_TABLE, max_polar=0,
                  block_threads=0, plane_begin=0, plane_end=0, kernel=0, chunk_cap=0, cache_groups=0, persistent=0,
-                 lib=None):
+                 family_begin=0, family_end=0, lib=None):
         self.lib = lib or load_library()
         self.arrays = arrays
         self.problem, self._keep = problem_from_arrays(arrays)
@@ -173,6 +194,7 @@ class Sweeper:
         opt.chunk_cap = chunk_cap
         opt.cache_groups = cache_groups
         opt.persistent = persistent
+        opt.family_begin, opt.family_end = family_begin, family_end
         self.h = C.c_void_p()
         rc = self.lib.mocb200_create(C.byref(self.problem), C.byref(opt), C.byref(self.h))
         if rc != 0:
@@ -241,6 +263,23 @@ class Sweeper:
 
     def sweep(self, g_begin, g_count, n_inner=1, tally_mode=TALLY_NONE, use_qbar=False):
         self._ck(self.lib.mocb200_sweep(self.h, g_begin, g_count, n_inner, tally_mode, int(use_qbar)), "sweep")
+
+    def sweep_partial(self, g_begin, g_count=1, tally_mode=TALLY_NONE, use_qbar=False):
+        """One inner sweep of the handle's angle families; the tally stays un-normalised (sum it over the ranks,
+        then finalize_flux)."""
+        self._ck(self.lib.mocb200_sweep_partial(self.h, g_begin, g_count, tally_mode, int(use_qbar)), "sweep_partial")
+
+    def finalize_flux(self, g_begin, g_count=1):
+        self._ck(self.lib.mocb200_finalize_flux(self.h, g_begin, g_count), "finalize_flux")
+
+    def device_buffer(self, which):
+        """(device address, doubles) of BUF_TALLY / BUF_CURRENT / BUF_SURFACE_FLUX."""
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.mocb200_device_buffer(self.h, which, C.byref(p), C.byref(n)), "device_buffer")
+        return p.value, n.value
+
+    def adopt_device_buffer(self, which, device_ptr, count):
+        self._ck(self.lib.mocb200_adopt_device_buffer(self.h, which, C.c_void_p(device_ptr), count), "adopt_device_buffer")
 
     def get_coarse(self, group):
         cur = np.zeros(self.n_surf)

@@ -149,6 +149,8 @@ struct mocb200_sweeper {
     std::vector<int> ev_inners; // inner sweeps an event pair brackets (persistent launches: several)
     size_t ev_used = 0;
     // persistent register-chunk sweep (all plain inners of a call in one cooperative launch)
+    int n_family = 1;            // angle families of the problem (angle_families)
+    bool family_partial = false; // this handle sweeps a proper subset of them: flux needs the tallies of the others
     int rc_interleave = 1; // MOCB200_RC_INTERLEAVE=0|1 (A/B hook)
     int persist_mode = 0; // 0: one launch per boundary phase; 1: persistent; 2: + requests in front of the grid barriers
     unsigned int *d_gridbar = nullptr;
@@ -566,6 +568,62 @@ int validate(const mocb200_problem *p)
     return MOCB200_OK;
 }
 
+// ANGLE FAMILIES (sharding one 2-D plane over ranks): sets of sweep angles closed under everything
+// that couples angles inside a sweep -- the two directions of a track (a, a + n_ang), the polar copies the kernels
+// bundle (same azimuth), and the boundary update (boundary_condition.cpp:155-191: the outgoing face of angle a feeds
+// the incoming face of reflect(a, normal)). On a product quadrature a family is one azimuth of octant 1, its mirror
+// image in octant 2, all their polar copies and their reverses: C5G7-2D has 8. A handle restricted to a family range
+// sweeps its tracks exactly as the whole sweep does (Gauss-Seidel order included); what couples the ranks is the FSR
+// tally (and the coarse tallies), summed over ranks between sweep and flux update.
+int angle_families(const mocb200_problem &p, std::vector<int> &family)
+{
+    const int nab = 2 * p.n_ang;
+    std::vector<int> parent(nab);
+    for (int i = 0; i < nab; i++)
+        parent[i] = i;
+    auto find = [&](int x) {
+        while (parent[x] != x)
+            x = parent[x] = parent[parent[x]];
+        return x;
+    };
+    auto unite = [&](int a, int b) {
+        a = find(a), b = find(b);
+        if (a != b)
+            parent[std::max(a, b)] = std::min(a, b);
+    };
+    for (int a = 0; a < p.n_ang; a++)
+        unite(a, a + p.n_ang);
+    // polar copies: angles of one octant whose rays have the same boundary layout and the same azimuth (same X / Y
+    // face sizes and the same ray spacing areas)
+    for (int oct = 0; oct < 2; oct++)
+        for (int a = oct * p.ndir_oct; a < (oct + 1) * p.ndir_oct; a++)
+            for (int b = a + 1; b < (oct + 1) * p.ndir_oct; b++)
+                if (p.bc_size_x[a] == p.bc_size_x[b] && p.bc_size_y[a] == p.bc_size_y[b] &&
+                    p.ang_area_x[a] == p.ang_area_x[b] && p.ang_area_y[a] == p.ang_area_y[b])
+                    unite(a, b);
+    for (int ao = 0; ao < nab; ao++)
+        for (int face = 0; face < 2; face++) {
+            if (p.bc_dst_kind[2 * ao + face] == 2)
+                continue;
+            const int dst = p.bc_dst_off[2 * ao + face];
+            for (int t = 0; t < nab; t++)
+                if (dst >= p.bc_offset[t] && dst < p.bc_offset[t] + p.bc_size_x[t] + p.bc_size_y[t]) {
+                    unite(ao, t);
+                    break;
+                }
+        }
+    family.assign(nab, -1);
+    int n = 0;
+    std::vector<int> id(nab, -1);
+    for (int i = 0; i < nab; i++) {
+        const int r = find(i);
+        if (id[r] < 0)
+            id[r] = n++;
+        family[i] = id[r];
+    }
+    return n;
+}
+
 int build(mocb200_sweeper *h, const mocb200_problem &p)
 {
     const mocb200_options &opt = h->opt;
@@ -689,6 +747,32 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
     };
     make_bundles(false, bundles, bundle_phase, bundle_geom);
     make_bundles(true, tbundles, tbundle_phase, tbundle_geom);
+    // angle-family range of this handle: bundles outside it are dropped (a bundle never straddles families)
+    {
+        std::vector<int> family;
+        h->n_family = angle_families(p, family);
+        if (opt.family_begin != 0 || opt.family_end != 0) {
+            if (opt.family_begin < 0 || opt.family_end > h->n_family || opt.family_begin >= opt.family_end)
+                return fail(h, MOCB200_ERR_INVALID, "bad angle-family range [%d, %d) of %d", opt.family_begin,
+                            opt.family_end, h->n_family);
+            h->family_partial = opt.family_end - opt.family_begin < h->n_family;
+            auto keep = [&](std::vector<Bundle> &bs, std::vector<int> &ph, std::vector<int> &ge) {
+                size_t w = 0;
+                for (size_t b = 0; b < bs.size(); b++) {
+                    const int f = family[bs[b].ang[0]];
+                    for (int q = 1; q < bs[b].np; q++)
+                        if (family[bs[b].ang[q]] != f)
+                            return false;
+                    if (f >= opt.family_begin && f < opt.family_end)
+                        bs[w] = bs[b], ph[w] = ph[b], ge[w] = ge[b], w++;
+                }
+                bs.resize(w), ph.resize(w), ge.resize(w);
+                return true;
+            };
+            if (!keep(bundles, bundle_phase, bundle_geom) || !keep(tbundles, tbundle_phase, tbundle_geom))
+                return fail(h, MOCB200_ERR_INVALID, "a polar bundle straddles two angle families");
+        }
+    }
     if (h->kernel == MOCB200_KERNEL_RCHUNK) { // one lane per polar angle: bundles of 1, 2 or 4; 8-bit flags + angle in 32 bits
         bool ok = p.n_ang < (1 << 23);
         for (const auto &b : tbundles)
@@ -1690,7 +1774,101 @@ int mocb200_get_boundary(mocb200_sweeper *h, int plane, int g_begin, int g_count
     return download_columns(h, bc, h->bcpg, g_begin, g_count, h->d_bc[h->bc_cur] + off);
 }
 
+} // extern "C"
+
+// finalize == false: one inner sweep that leaves the FSR tally un-normalised (mocb200_sweep_partial)
+static int sweep_impl(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int tally_mode, int use_qbar, bool finalize);
+
+extern "C" {
+
 int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int tally_mode, int use_qbar)
+{
+    if (h && h->family_partial)
+        return fail(h, MOCB200_ERR_STATE, "this handle sweeps a subset of the angle families: use mocb200_sweep_partial, "
+                                          "sum the tallies over the ranks, then mocb200_finalize_flux");
+    return sweep_impl(h, g_begin, g_count, n_inner, tally_mode, use_qbar, true);
+}
+
+int mocb200_sweep_partial(mocb200_sweeper *h, int g_begin, int g_count, int tally_mode, int use_qbar)
+{
+    if (h && g_count > 2)
+        return fail(h, MOCB200_ERR_INVALID, "mocb200_sweep_partial: at most two groups per call (per-group sweep kernels)");
+    if (h && tally_mode == MOCB200_TALLY_CORRECTIONS)
+        return fail(h, MOCB200_ERR_INVALID, "mocb200_sweep_partial: the 2D3D correction factors need every angle on one handle");
+    return sweep_impl(h, g_begin, g_count, 1, tally_mode, use_qbar, false);
+}
+
+int mocb200_finalize_flux(mocb200_sweeper *h, int g_begin, int g_count)
+{
+    int rc = check_groups(h, g_begin, g_count);
+    if (rc)
+        return rc;
+    if (g_count > 2)
+        return fail(h, MOCB200_ERR_INVALID, "mocb200_finalize_flux: at most two groups per call");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const bool cached = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK || h->kernel == MOCB200_KERNEL_RCHUNK;
+    const bool rchunk = h->kernel == MOCB200_KERNEL_RCHUNK;
+    const int64_t nrg = (int64_t)(h->reg_hi - h->reg_lo) * g_count;
+    finalize_flux_q_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
+        h->n_reg, h->GP, g_begin, g_count, cached ? h->d_tg : h->d_tally, h->d_xstr, h->d_vol, h->d_qbar, h->d_flux, h->reg_lo,
+        h->reg_hi, cached ? 1 : 0, rchunk ? h->d_fsr_perm : nullptr, h->n_regp);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return MOCB200_OK;
+}
+
+int mocb200_angle_families(const mocb200_problem *prob, int32_t *n_family, int32_t *family_of_angle)
+{
+    if (!prob || !n_family)
+        return MOCB200_ERR_INVALID;
+    std::vector<int> fam;
+    *n_family = angle_families(*prob, fam);
+    if (family_of_angle)
+        for (int i = 0; i < 2 * prob->n_ang; i++)
+            family_of_angle[i] = fam[i];
+    return MOCB200_OK;
+}
+
+int mocb200_device_buffer(mocb200_sweeper *h, int which, void **ptr, int64_t *count)
+{
+    if (!h || !ptr || !count)
+        return MOCB200_ERR_INVALID;
+    const bool cached = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK || h->kernel == MOCB200_KERNEL_RCHUNK;
+    switch (which) {
+    case MOCB200_BUF_TALLY:
+        *ptr   = cached ? h->d_tg : h->d_tally;
+        *count = cached ? (int64_t)h->G * std::max(h->n_reg, h->n_regp) : (int64_t)h->n_reg * h->GP;
+        return MOCB200_OK;
+    case MOCB200_BUF_CURRENT: *ptr = h->d_current, *count = (int64_t)h->n_surf * h->GP; return MOCB200_OK;
+    case MOCB200_BUF_SURFACE_FLUX: *ptr = h->d_surfflux, *count = (int64_t)h->n_surf * h->GP; return MOCB200_OK;
+    }
+    return fail(h, MOCB200_ERR_INVALID, "unknown device buffer %d", which);
+}
+
+int mocb200_adopt_device_buffer(mocb200_sweeper *h, int which, void *ptr, int64_t count)
+{
+    void *old    = nullptr;
+    int64_t need = 0;
+    int rc       = mocb200_device_buffer(h, which, &old, &need);
+    if (rc)
+        return rc;
+    if (!ptr || count < need)
+        return fail(h, MOCB200_ERR_INVALID, "adopted buffer holds %lld doubles, %lld needed", (long long)count, (long long)need);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemcpy(ptr, old, (size_t)need * sizeof(double), cudaMemcpyDeviceToDevice));
+    const bool cached = h->kernel == MOCB200_KERNEL_CACHED || h->kernel == MOCB200_KERNEL_CHUNK || h->kernel == MOCB200_KERNEL_RCHUNK;
+    switch (which) { // the handle's own allocation stays in its list and is freed with the handle
+    case MOCB200_BUF_TALLY: (cached ? h->d_tg : h->d_tally) = (double *)ptr; break;
+    case MOCB200_BUF_CURRENT: h->d_current = (double *)ptr; break;
+    case MOCB200_BUF_SURFACE_FLUX: h->d_surfflux = (double *)ptr; break;
+    }
+    return MOCB200_OK;
+}
+
+} // extern "C"
+
+static int sweep_impl(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int tally_mode, int use_qbar, bool finalize)
 {
     int rc = check_groups(h, g_begin, g_count);
     if (rc)
@@ -1818,7 +1996,7 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
 
     // ---- persistent path: every plain inner of this call in one cooperative launch (moc_rchunk_kernel.cuh) ----
     int inner0 = 0;
-    if (rchunk && !use_qbar && h->n_counters <= 256 && h->persist_mode > 0) {
+    if (rchunk && !use_qbar && h->n_counters <= 256 && h->persist_mode > 0 && finalize) {
         const TrackList *pl[2] = {nullptr, nullptr};
         int n_in_phase[2]      = {0, 0};
         for (const auto &tl : h->tlists)
@@ -2100,6 +2278,10 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
         }
         if (jacobi)
             h->bc_cur = 1 - h->bc_cur;
+        if (!finalize) { // mocb200_sweep_partial: the caller sums the tally over the ranks, then mocb200_finalize_flux
+            CUDA_TRY(h, cudaGetLastError());
+            continue;
+        }
         if (fuse_q && !last)
             finalize_next_q_kernel<<<grid_for(nrg, 256, h->sm_count), 256, 0, h->stream>>>(
                 h->n_reg, h->GP, g_begin, g_count, h->d_tg, h->d_xstr, h->d_vol, h->d_qbar, h->d_flux, h->reg_lo,
@@ -2114,6 +2296,8 @@ int mocb200_sweep(mocb200_sweeper *h, int g_begin, int g_count, int n_inner, int
     }
     return MOCB200_OK;
 }
+
+extern "C" {
 
 int mocb200_set_sweep_inputs(mocb200_sweeper *h, int group, const double *source, const double *flux,
                              const double *const *boundary)

@@ -1,4 +1,4 @@
-"""Plane sharding of the MoC sweep across GPUs / ranks (host-side logic).
+"""Sharding of the MoC sweep across GPUs / ranks (host-side logic): macroplanes, and angle families of one plane.
 
 Inside a sweep the macroplanes are independent (reference: src/sweepers/moc/moc_sweeper_kernel.inc.hpp:51-153
 loops planes outermost and every plane touches only its own boundary condition, FSR range and coarse-surface
@@ -62,3 +62,35 @@ def all_gather_flux(local_flux, arrays, ranges, rank, dist_module):
         a, b = reg_range(arrays, rng)
         full[..., a:b] = recv[r][..., : b - a].numpy()
     return full
+
+
+# ---- angle families: one 2-D plane over several ranks ("for single-plane 2-D cases") ----
+# A family (mocb200_angle_families) is closed under track reversal, polar bundling and the boundary update
+# (boundary_condition.cpp:155-191), so a rank sweeps its families exactly as the whole sweep does, Gauss-Seidel
+# order included, and NO boundary flux travels. What the reference sums over its threads -- the per-FSR tally t_flux,
+# moc_sweeper_kernel.inc.hpp:155-163 -- is summed over the ranks (all-reduce), then every rank applies the flux
+# update (:165-173). The coarse tallies of the last inner are summed the same way.
+
+def family_weights(arrays, family):
+    """Segments swept per angle family (forward angles only: a track is swept in both directions)."""
+    n_ang = int(arrays["n_ang"][0])
+    gtb, tsb, ang_geom = arrays["geom_trk_begin"], arrays["trk_seg_begin"], arrays["ang_geom"]
+    w = np.zeros(int(np.max(family)) + 1)
+    for a in range(n_ang):
+        g = int(ang_geom[a])
+        w[family[a]] += float(tsb[gtb[g + 1]] - tsb[gtb[g]])
+    return w
+
+
+def partition_families(arrays, family, n_parts):
+    """Contiguous family ranges [(begin, end), ...] balancing the segments swept."""
+    return partition_planes(family_weights(arrays, family), n_parts)
+
+
+def allreduce_sum(x, dist_module):
+    """Sum of a float64 array over the ranks (gloo on CPU; on GPUs the device buffers the handle adopted are
+    all-reduced in place over NCCL, bench.py --shard angles)."""
+    import torch
+    t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).clone()
+    dist_module.all_reduce(t)
+    return t.numpy()

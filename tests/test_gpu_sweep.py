@@ -528,3 +528,91 @@ def test_sliding_attenuation_cache_equals_full_cache(case, slots):
         sw.close()
     for x, y in zip(*res):
         _close(x, y, atol=1e-13)
+
+
+@pytest.mark.parametrize("case,parts", [("mini2d_gs", 2), ("3x3_s05_gs", 3)])
+@pytest.mark.parametrize("tally", [0, 1])
+def test_angle_family_sharding_equals_whole_sweep(case, parts, tally):
+    """One plane split over `parts` handles by angle families (mocb200_options.family_begin/end): every handle sweeps
+    its families (mocb200_sweep_partial), the FSR tallies and the coarse tallies are summed over the handles -- here
+    on one GPU through adopted torch tensors, across ranks bench.py --shard angles all-reduces the same buffers over
+    NCCL --, then mocb200_finalize_flux. Three inner iterations, Gauss-Seidel boundary update: flux, coarse tallies and
+    the boundary flux of every family equal the single-handle sweep."""
+    import torch
+    from mocc_b200.capi import BUF_CURRENT, BUF_SURFACE_FLUX, BUF_TALLY, angle_families
+    from mocc_b200.sharding import partition_families
+    flat, gold = load_case(case)
+    G, n_reg, bcpg = (int(flat[k][0]) for k in ("n_group", "n_reg", "bc_per_group"))
+    n_fam, fam = angle_families(flat)
+    ranges = partition_families(flat, fam, parts)
+    assert len(ranges) == parts
+    g, n_inner = 1, 3
+    rng = np.random.default_rng(3)
+    xstr, xself = gold[f"xs_tr_{g}"], gold[f"xs_self_{g}"]
+    src = rng.uniform(0.05, 1.0, size=n_reg)
+    flux0 = rng.uniform(0.5, 1.5, size=n_reg)
+    bc = rng.uniform(0.0, 0.3, size=bcpg)
+
+    def setup(**kw):
+        sw = _sweeper(flat, boundary_update=0, **kw)
+        sw.set_xs(g, xstr, xstr_src=xstr, xs_self=xself)
+        sw.set_source(g, src)
+        sw.set_flux(g, flux0)
+        sw.set_boundary(0, g, bc)
+        return sw
+    whole = setup()
+    whole.sweep(g, 1, n_inner=n_inner, tally_mode=tally)
+    ref_flux, ref_bc = whole.get_flux(g, 1)[0], whole.get_boundary(0, g, 1)[0]
+    ref_coarse = whole.get_coarse(g) if tally else None
+    with pytest.raises(RuntimeError):  # a partial handle refuses the whole-sweep entry point
+        s = setup(family_begin=ranges[0][0], family_end=ranges[0][1])
+        try:
+            s.sweep(g, 1)
+        finally:
+            s.close()
+    whole.close()
+
+    handles = [setup(family_begin=b, family_end=e) for b, e in ranges]
+    bufs = []
+    for sw in handles:
+        mine = {}
+        for which in (BUF_TALLY, BUF_CURRENT, BUF_SURFACE_FLUX):
+            _, n = sw.device_buffer(which)
+            t = torch.zeros(n, dtype=torch.float64, device="cuda")
+            sw.adopt_device_buffer(which, t.data_ptr(), n)
+            mine[which] = t
+        bufs.append(mine)
+
+    def reduce_over_handles(which):
+        for sw in handles:
+            sw.synchronize()
+        total = sum(b[which] for b in bufs)
+        for b in bufs:
+            b[which].copy_(total)
+        torch.cuda.synchronize()
+    for inner in range(n_inner):
+        last = inner == n_inner - 1
+        for sw in handles:
+            sw.sweep_partial(g, 1, tally_mode=tally if last else 0)
+        reduce_over_handles(BUF_TALLY)
+        if last and tally:
+            reduce_over_handles(BUF_CURRENT)
+            reduce_over_handles(BUF_SURFACE_FLUX)
+        for sw in handles:
+            sw.finalize_flux(g, 1)
+    # boundary slots of a family belong to the handle that sweeps it
+    off, sx, sy = flat["bc_offset"], flat["bc_size_x"], flat["bc_size_y"]
+    got_bc = np.full(bcpg, np.nan)
+    for sw, (b, e) in zip(handles, ranges):
+        _close(sw.get_flux(g, 1)[0], ref_flux, rtol=1e-11)
+        if tally:
+            for x, y in zip(sw.get_coarse(g), ref_coarse):
+                _close(x, y, rtol=1e-10, atol=1e-12)
+        mine = sw.get_boundary(0, g, 1)[0]
+        for ao in range(len(fam)):
+            if b <= fam[ao] < e:
+                sl = slice(int(off[ao]), int(off[ao] + sx[ao] + sy[ao]))
+                got_bc[sl] = mine[sl]
+        sw.close()
+    assert not np.isnan(got_bc).any()
+    _close(got_bc, ref_bc, rtol=1e-11)

@@ -89,3 +89,96 @@ def test_stacked_planes_sweep_like_the_single_plane():
         if mode == 1:  # radial surfaces of the plane (the first nx*ny of every plane's range are its bottom faces)
             assert np.array_equal(curN[ip * nsp + nxy:(ip + 1) * nsp], cur1[nxy:nsp])
             assert np.array_equal(sfN[ip * nsp + nxy:(ip + 1) * nsp], sf1[nxy:nsp])
+
+
+# ---- angle families (one plane over several ranks) ----
+
+def _families_py(flat):
+    """Independent restatement of the closure the C ABI computes: union-find over track reversal, polar copies of an
+    azimuth and the boundary-update destinations."""
+    n_ang = int(flat["n_ang"][0])
+    nab, ndo = 2 * n_ang, int(flat["ndir_oct"][0])
+    parent = list(range(nab))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    def unite(a, b):
+        a, b = find(a), find(b)
+        if a != b:
+            parent[max(a, b)] = min(a, b)
+    off, sx, sy = flat["bc_offset"], flat["bc_size_x"], flat["bc_size_y"]
+    for a in range(n_ang):
+        unite(a, a + n_ang)
+    for o in range(2):
+        for a in range(o * ndo, (o + 1) * ndo):
+            for b in range(a + 1, (o + 1) * ndo):
+                if abs(flat["ang_alpha"][a] - flat["ang_alpha"][b]) < 1e-12:
+                    unite(a, b)
+    for ao in range(nab):
+        for face in range(2):
+            if flat["bc_dst_kind"][2 * ao + face] == 2:
+                continue
+            dst = int(flat["bc_dst_off"][2 * ao + face])
+            t = next(t for t in range(nab) if off[t] <= dst < off[t] + sx[t] + sy[t])
+            unite(ao, t)
+    roots = sorted({find(i) for i in range(nab)})
+    return [roots.index(find(i)) for i in range(nab)]
+
+
+@pytest.mark.parametrize("case", ["mini2d_gs", "3x3_s05_gs", "mini3d_gs"])
+def test_angle_families_are_closed_under_reversal_and_boundary_update(case):
+    from mocc_b200.capi import angle_families
+    flat, _ = load_case(case)
+    n, fam = angle_families(flat)
+    assert list(fam) == _families_py(flat)
+    assert n == max(fam) + 1 and n > 1
+    # every family holds angles of both boundary phases (octants 1 and 2): the Gauss-Seidel order survives
+    n_ang, ndo = int(flat["n_ang"][0]), int(flat["ndir_oct"][0])
+    for f in range(n):
+        members = [a for a in range(n_ang) if fam[a] == f]
+        assert any(a < ndo for a in members) and any(a >= ndo for a in members)
+
+
+def _family_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from mocc_b200.capi import angle_families
+    from mocc_b200.sharding import allreduce_sum, partition_families
+    from oracle_lib import oracle_sweep1g
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat, gold = load_case("mini2d_gs")
+    rec = records(gold)[0]
+    n_ang = int(flat["n_ang"][0])
+    n, fam = angle_families(flat)
+    lo, hi = partition_families(flat, fam, world)[rank]
+    # the rank's share of the sweep: the oracle (test infrastructure) with the tally weights of the other families'
+    # angles set to zero leaves exactly this rank's partial t_flux behind
+    mine = dict(flat)
+    mine["wt_v_st"] = np.where([lo <= fam[a] < hi for a in range(n_ang)], flat["wt_v_st"], 0.0)
+    flux_part, bc_out, _, _ = oracle_sweep1g(mine, rec["xstr"], rec["qbar"], rec["bc_in"], gs_boundary=True)
+    fpi = 4.0 * np.pi
+    partial = (flux_part - rec["qbar"] * fpi) * (rec["xstr"] * flat["vol"])   # t_flux of my angles
+    tally = allreduce_sum(partial, dist)                                          # kernel:155-163 across ranks
+    flux = tally / (rec["xstr"] * flat["vol"]) + rec["qbar"] * fpi                # kernel:165-173
+    np.save(os.path.join(out_dir, f"aflux_{rank}.npy"), flux)
+    np.save(os.path.join(out_dir, f"abc_{rank}.npy"), bc_out)
+    dist.destroy_process_group()
+
+
+def test_two_ranks_sum_angle_family_tallies(tmp_path):
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_family_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    flat, gold = load_case("mini2d_gs")
+    rec = records(gold)[0]
+    for r in range(2):
+        flux = np.load(tmp_path / f"aflux_{r}.npy")
+        assert np.max(np.abs(flux - rec["flux_out"]) / rec["flux_out"]) < 1e-12
+        assert np.array_equal(np.load(tmp_path / f"abc_{r}.npy").reshape(-1), rec["bc_out"].reshape(-1))
