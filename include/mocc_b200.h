@@ -34,6 +34,7 @@
 #ifndef MOCC_B200_H
 #define MOCC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -206,6 +207,30 @@ int mocb200_set_xs(mocb200_sweeper *h, int g_begin, int g_count, const double *x
 int mocb200_set_source(mocb200_sweeper *h, int g_begin, int g_count, const double *src);
 int mocb200_set_flux(mocb200_sweeper *h, int g_begin, int g_count, const double *flux);
 int mocb200_get_flux(mocb200_sweeper *h, int g_begin, int g_count, double *flux);
+int mocb200_get_source(mocb200_sweeper *h, int g_begin, int g_count, double *src);
+/*
+ * SOURCE CONSTRUCTION ON THE DEVICE: what FixedSourceSolver::step does on the host before every
+ * sweep(group) (src/solvers/fixed_source_solver.cpp:102-117) and EigenSolver::step before that
+ * (src/solvers/eigen_solver.cpp:218-245), from the flux resident on the device -- no source or flux upload per group.
+ *   mocb200_set_source_xs        cross sections by cross-section-mesh region: fsr_mat [n_reg] region of every FSR,
+ *                                xsnf / xsch [n_mat][n_group], scat [n_mat][to][from], scat_band [n_mat][to][2] = the
+ *                                row's ScatteringRow::min_g / max_g (NULL: first / last non-zero entry)
+ *   mocb200_set_external_source  Source::add_external's [n_group][n_reg] array (NULL: none; source.cpp:41-54)
+ *   mocb200_fission_source       TransportSweeper::calc_fission_source (src/core/transport_sweeper.cpp:119-134):
+ *                                fs = sum_g (1/k nu-Sigma_f,g) flux_g from the resident flux
+ *   mocb200_set/get_fission_source   the host's array instead / for the host's convergence test
+ *   mocb200_build_source         Source::initialize_group + fission + in_scatter (src/core/source.cpp:41-112) for groups
+ *                                [g_begin, g_begin + g_count) into the source mocb200_sweep reads. Group g sees the flux
+ *                                of the groups swept before it (Gauss-Seidel over groups) when called group by group
+ * Same operations in the same order as the reference, not contracted: bit-identical to its host arrays.
+ */
+int mocb200_set_source_xs(mocb200_sweeper *h, int n_mat, const int32_t *fsr_mat, const double *xsnf, const double *xsch,
+                          const double *scat, const int32_t *scat_band);
+int mocb200_set_external_source(mocb200_sweeper *h, const double *ext);
+int mocb200_fission_source(mocb200_sweeper *h, double k);
+int mocb200_set_fission_source(mocb200_sweeper *h, const double *fs);
+int mocb200_get_fission_source(mocb200_sweeper *h, double *fs);
+int mocb200_build_source(mocb200_sweeper *h, int g_begin, int g_count);
 /* Directly impose q-bar (skips self scatter on the next sweep with n_inner == 1 and
  * use_qbar != 0); for sweep1g-level parity tests. [g_count][n_reg] */
 int mocb200_set_qbar(mocb200_sweeper *h, int g_begin, int g_count, const double *qbar);

@@ -134,6 +134,14 @@ def load_library(path=None):
     lib.mocb200_last_sweep_ms.argtypes = [H, _f64p]
     lib.mocb200_set_timing.argtypes = [H, C.c_int]
     lib.mocb200_get_timing.argtypes = [H, _f64p, C.POINTER(C.c_int64)]
+    i32p = C.POINTER(C.c_int32)
+    lib.mocb200_get_source.argtypes = [H, C.c_int, C.c_int, _f64p]
+    lib.mocb200_set_source_xs.argtypes = [H, C.c_int, i32p, _f64p, _f64p, _f64p, i32p]
+    lib.mocb200_set_external_source.argtypes = [H, _f64p]
+    lib.mocb200_fission_source.argtypes = [H, C.c_double]
+    lib.mocb200_set_fission_source.argtypes = [H, _f64p]
+    lib.mocb200_get_fission_source.argtypes = [H, _f64p]
+    lib.mocb200_build_source.argtypes = [H, C.c_int, C.c_int]
     lib.mocb200_angle_families.argtypes = [C.POINTER(Problem), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.mocb200_sweep_partial.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.mocb200_finalize_flux.argtypes = [H, C.c_int, C.c_int]
@@ -150,6 +158,18 @@ def _ptr(a):
 
 
 BUF_TALLY, BUF_CURRENT, BUF_SURFACE_FLUX = 0, 1, 2
+
+
+def material_tables(xs_nf, xs_ch, xs_scat):
+    """Cross-section-mesh regions out of per-FSR arrays (what a flattened problem carries): xs_nf / xs_ch [G][n_reg],
+    xs_scat [G to][G from][n_reg] -> (fsr_mat [n_reg] int32, xsnf [n_mat][G], xsch [n_mat][G], scat [n_mat][to][from]).
+    The C++ plugin passes the reference's XSMesh regions directly."""
+    xs_nf, xs_ch, xs_scat = (np.asarray(a, dtype=np.float64) for a in (xs_nf, xs_ch, xs_scat))
+    G, n_reg = xs_nf.shape
+    cols = np.concatenate([xs_nf, xs_ch, xs_scat.reshape(G * G, n_reg)], axis=0).T  # one row per FSR
+    uniq, inv = np.unique(cols, axis=0, return_inverse=True)
+    return (np.ascontiguousarray(inv.reshape(-1), dtype=np.int32), np.ascontiguousarray(uniq[:, :G]),
+            np.ascontiguousarray(uniq[:, G:2 * G]), np.ascontiguousarray(uniq[:, 2 * G:].reshape(-1, G, G)))
 
 
 def angle_families(arrays, lib=None):
@@ -263,6 +283,47 @@ class Sweeper:
 
     def sweep(self, g_begin, g_count, n_inner=1, tally_mode=TALLY_NONE, use_qbar=False):
         self._ck(self.lib.mocb200_sweep(self.h, g_begin, g_count, n_inner, tally_mode, int(use_qbar)), "sweep")
+
+    # ---- source construction on the device (FixedSourceSolver::step / calc_fission_source) ----
+    def set_source_xs(self, fsr_mat, xsnf, xsch, scat, band=None):
+        fsr_mat = np.ascontiguousarray(fsr_mat, dtype=np.int32)
+        xsnf, xsch, scat = (np.ascontiguousarray(a, dtype=np.float64) for a in (xsnf, xsch, scat))
+        n_mat, G = xsnf.shape
+        assert fsr_mat.size == self.n_reg and G == self.n_group and xsch.shape == (n_mat, G) and scat.shape == (n_mat, G, G)
+        i32p = C.POINTER(C.c_int32)
+        if band is not None:
+            band = np.ascontiguousarray(band, dtype=np.int32)
+            assert band.shape == (n_mat, G, 2)
+        self._ck(self.lib.mocb200_set_source_xs(self.h, n_mat, fsr_mat.ctypes.data_as(i32p), _ptr(xsnf), _ptr(xsch),
+                                                _ptr(scat), band.ctypes.data_as(i32p) if band is not None else None),
+                 "set_source_xs")
+
+    def set_external_source(self, ext):
+        if ext is None:
+            self._ck(self.lib.mocb200_set_external_source(self.h, None), "set_external_source")
+        else:
+            ext = _host(ext, (self.n_group, self.n_reg))
+            self._ck(self.lib.mocb200_set_external_source(self.h, _ptr(ext)), "set_external_source")
+
+    def fission_source(self, k):
+        self._ck(self.lib.mocb200_fission_source(self.h, float(k)), "fission_source")
+
+    def set_fission_source(self, fs):
+        fs = _host(fs, (self.n_reg,))
+        self._ck(self.lib.mocb200_set_fission_source(self.h, _ptr(fs)), "set_fission_source")
+
+    def get_fission_source(self):
+        fs = np.empty(self.n_reg)
+        self._ck(self.lib.mocb200_get_fission_source(self.h, _ptr(fs)), "get_fission_source")
+        return fs
+
+    def build_source(self, g_begin, g_count=1):
+        self._ck(self.lib.mocb200_build_source(self.h, g_begin, g_count), "build_source")
+
+    def get_source(self, g_begin, g_count):
+        out = np.empty((g_count, self.n_reg))
+        self._ck(self.lib.mocb200_get_source(self.h, g_begin, g_count, _ptr(out)), "get_source")
+        return out
 
     def sweep_partial(self, g_begin, g_count=1, tally_mode=TALLY_NONE, use_qbar=False):
         """One inner sweep of the handle's angle families; the tally stays un-normalised (sum it over the ranks,

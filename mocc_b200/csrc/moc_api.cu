@@ -149,6 +149,11 @@ struct mocb200_sweeper {
     std::vector<int> ev_inners; // inner sweeps an event pair brackets (persistent launches: several)
     size_t ev_used = 0;
     // persistent register-chunk sweep (all plain inners of a call in one cooperative launch)
+    // device-side source construction (mocb200_set_source_xs)
+    int n_mat = 0;
+    int32_t *d_fsr_mat = nullptr, *d_scat_band = nullptr;
+    double *d_mat_nf = nullptr, *d_mat_ch = nullptr, *d_mat_scat = nullptr, *d_fs = nullptr, *d_ext = nullptr;
+    bool have_fs = false;
     int n_family = 1;            // angle families of the problem (angle_families)
     bool family_partial = false; // this handle sweeps a proper subset of them: flux needs the tallies of the others
     int rc_interleave = 1; // MOCB200_RC_INTERLEAVE=0|1 (A/B hook)
@@ -1734,6 +1739,146 @@ COLUMN_SETTER(mocb200_set_source, d_src)
 COLUMN_SETTER(mocb200_set_flux, d_flux)
 COLUMN_SETTER(mocb200_set_qbar, d_qbar)
 #undef COLUMN_SETTER
+
+int mocb200_get_source(mocb200_sweeper *h, int g_begin, int g_count, double *src)
+{
+    int rc = check_groups(h, g_begin, g_count);
+    if (rc)
+        return rc;
+    if (!src)
+        return fail(h, MOCB200_ERR_INVALID, "get_source: NULL array");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return download_columns(h, src, h->n_reg, g_begin, g_count, h->d_src);
+}
+
+int mocb200_set_source_xs(mocb200_sweeper *h, int n_mat, const int32_t *fsr_mat, const double *xsnf, const double *xsch,
+                          const double *scat, const int32_t *scat_band)
+{
+    if (!h)
+        return MOCB200_ERR_INVALID;
+    if (n_mat < 1 || !fsr_mat || !xsnf || !xsch || !scat)
+        return fail(h, MOCB200_ERR_INVALID, "set_source_xs: NULL table or no material");
+    const int G = h->G;
+    for (int r = 0; r < h->n_reg; r++)
+        if (fsr_mat[r] < 0 || fsr_mat[r] >= n_mat)
+            return fail(h, MOCB200_ERR_INVALID, "set_source_xs: FSR %d has cross-section region %d of %d", r, fsr_mat[r], n_mat);
+    std::vector<int32_t> band((size_t)n_mat * G * 2);
+    for (int m = 0; m < n_mat; m++)
+        for (int g = 0; g < G; g++) {
+            int lo = G, hi = -1; // ScatteringRow: first / last non-zero entry of the row (scattering_matrix.cpp:40-62)
+            if (scat_band) {
+                lo = scat_band[((size_t)m * G + g) * 2], hi = scat_band[((size_t)m * G + g) * 2 + 1];
+                if (lo < 0 || hi >= G)
+                    return fail(h, MOCB200_ERR_INVALID, "set_source_xs: scattering band [%d, %d] outside the groups", lo, hi);
+            } else {
+                for (int gg = 0; gg < G; gg++)
+                    if (scat[((size_t)m * G + g) * G + gg] != 0.0)
+                        lo = std::min(lo, gg), hi = std::max(hi, gg);
+            }
+            band[((size_t)m * G + g) * 2] = lo, band[((size_t)m * G + g) * 2 + 1] = hi;
+        }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int rc;
+    if (!h->d_fsr_mat && ((rc = dev_alloc(h, &h->d_fsr_mat, (size_t)h->n_reg)) || (rc = dev_alloc(h, &h->d_fs, (size_t)h->n_reg))))
+        return rc;
+    if (n_mat > h->n_mat) { // tables grow: the old ones stay in the handle's allocation list
+        if ((rc = dev_alloc(h, &h->d_mat_nf, (size_t)n_mat * G)) || (rc = dev_alloc(h, &h->d_mat_ch, (size_t)n_mat * G)) ||
+            (rc = dev_alloc(h, &h->d_mat_scat, (size_t)n_mat * G * G)) || (rc = dev_alloc(h, &h->d_scat_band, (size_t)n_mat * G * 2)))
+            return rc;
+    }
+    h->n_mat = std::max(h->n_mat, n_mat);
+    CUDA_TRY(h, cudaMemcpy(h->d_fsr_mat, fsr_mat, sizeof(int32_t) * h->n_reg, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_mat_nf, xsnf, sizeof(double) * n_mat * G, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_mat_ch, xsch, sizeof(double) * n_mat * G, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_mat_scat, scat, sizeof(double) * n_mat * G * G, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_scat_band, band.data(), sizeof(int32_t) * band.size(), cudaMemcpyHostToDevice));
+    h->stats.device_bytes = h->device_bytes;
+    return MOCB200_OK;
+}
+
+int mocb200_set_external_source(mocb200_sweeper *h, const double *ext)
+{
+    if (!h)
+        return MOCB200_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!ext) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        h->d_ext = nullptr; // stays in the allocation list
+        return MOCB200_OK;
+    }
+    int rc;
+    double *d = nullptr;
+    if ((rc = dev_alloc(h, &d, (size_t)h->n_reg * h->GP)))
+        return rc;
+    CUDA_TRY(h, cudaMemsetAsync(d, 0, sizeof(double) * h->n_reg * h->GP, h->stream));
+    if ((rc = upload_columns(h, ext, h->n_reg, 0, h->G, d)))
+        return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->d_ext = d;
+    return MOCB200_OK;
+}
+
+int mocb200_fission_source(mocb200_sweeper *h, double k)
+{
+    if (!h)
+        return MOCB200_ERR_INVALID;
+    if (!h->d_fsr_mat)
+        return fail(h, MOCB200_ERR_STATE, "mocb200_set_source_xs has not been called");
+    if (!(k > 0.0))
+        return fail(h, MOCB200_ERR_INVALID, "fission_source: k = %g", k);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    fission_source_kernel<<<grid_for(h->reg_hi - h->reg_lo, 256, h->sm_count), 256, 0, h->stream>>>(
+        h->reg_lo, h->reg_hi, h->G, h->GP, 1.0 / k, h->d_fsr_mat, h->d_mat_nf, h->d_flux, h->d_fs);
+    h->stats.kernel_launches++;
+    h->have_fs = true;
+    CUDA_TRY(h, cudaGetLastError());
+    return MOCB200_OK;
+}
+
+int mocb200_set_fission_source(mocb200_sweeper *h, const double *fs)
+{
+    if (!h || !fs)
+        return MOCB200_ERR_INVALID;
+    if (!h->d_fsr_mat)
+        return fail(h, MOCB200_ERR_STATE, "mocb200_set_source_xs has not been called");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemcpy(h->d_fs, fs, sizeof(double) * h->n_reg, cudaMemcpyHostToDevice));
+    h->have_fs = true;
+    return MOCB200_OK;
+}
+
+int mocb200_get_fission_source(mocb200_sweeper *h, double *fs)
+{
+    if (!h || !fs)
+        return MOCB200_ERR_INVALID;
+    if (!h->have_fs)
+        return fail(h, MOCB200_ERR_STATE, "no fission source on the device yet");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaMemcpy(fs, h->d_fs, sizeof(double) * h->n_reg, cudaMemcpyDeviceToHost));
+    return MOCB200_OK;
+}
+
+int mocb200_build_source(mocb200_sweeper *h, int g_begin, int g_count)
+{
+    int rc = check_groups(h, g_begin, g_count);
+    if (rc)
+        return rc;
+    if (!h->d_fsr_mat)
+        return fail(h, MOCB200_ERR_STATE, "mocb200_set_source_xs has not been called");
+    if (!h->have_fs)
+        return fail(h, MOCB200_ERR_STATE, "mocb200_fission_source / mocb200_set_fission_source has not been called");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int64_t n = (int64_t)(h->reg_hi - h->reg_lo) * g_count;
+    group_source_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, h->stream>>>(
+        h->reg_lo, h->reg_hi, h->G, h->GP, g_begin, g_count, h->d_fsr_mat, h->d_mat_ch, h->d_mat_scat, h->d_scat_band,
+        h->d_ext, h->d_fs, h->d_flux, h->d_src);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return MOCB200_OK;
+}
 
 int mocb200_get_flux(mocb200_sweeper *h, int g_begin, int g_count, double *flux)
 {

@@ -839,6 +839,50 @@ static __global__ void finalize_next_q_kernel(int n_reg, int GP, int g_begin, in
     }
 }
 
+// ---- source construction on the device ----
+// Cross sections by cross-section-mesh region (material): fsr_mat [n_reg], xsnf / xsch [n_mat][G],
+// scat [n_mat][G to][G from] with the band [lo, hi] of every row (ScatteringRow::min_g / max_g).
+// TransportSweeper::calc_fission_source (transport_sweeper.cpp:119-134): fs = 0; += (1/k * nu-Sigma_f,g) * flux_g, g ascending
+static __global__ void fission_source_kernel(int reg_lo, int reg_hi, int G, int GP, double rkeff,
+                                             const int32_t *__restrict__ fsr_mat, const double *__restrict__ xsnf,
+                                             const double *__restrict__ flux, double *__restrict__ fs)
+{
+    for (int r = reg_lo + blockIdx.x * blockDim.x + threadIdx.x; r < reg_hi; r += gridDim.x * blockDim.x) {
+        const double *nf = xsnf + (size_t)fsr_mat[r] * G;
+        double acc       = 0.0;
+        for (int g = 0; g < G; g++)
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(rkeff, nf[g]), flux[(size_t)r * GP + g]));
+        fs[r] = acc;
+    }
+}
+
+// What FixedSourceSolver::step builds before sweep(group) (fixed_source_solver.cpp:102-117): Source::initialize_group
+// (source.cpp:41-54: external source or 0) + Source::fission (:64-80: += chi_g fs) + Source::in_scatter (:86-112: the
+// row's band in ascending order without the self-scatter term, += Sigma_s(g' -> g) flux_g'). Reads the RESIDENT flux: the
+// groups already swept in this outer carry their new flux, as in the reference's Gauss-Seidel over groups.
+static __global__ void group_source_kernel(int reg_lo, int reg_hi, int G, int GP, int g_begin, int g_count,
+                                           const int32_t *__restrict__ fsr_mat, const double *__restrict__ xsch,
+                                           const double *__restrict__ scat, const int32_t *__restrict__ band,
+                                           const double *__restrict__ ext, const double *__restrict__ fs,
+                                           const double *__restrict__ flux, double *__restrict__ src)
+{
+    const int nr    = reg_hi - reg_lo;
+    const int64_t n = (int64_t)nr * g_count;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = reg_lo + (int)(i / g_count);
+        const int g = g_begin + (int)(i % g_count);
+        const int m = fsr_mat[r];
+        double s_   = ext ? ext[(size_t)r * GP + g] : 0.0;
+        s_          = __dadd_rn(s_, __dmul_rn(xsch[(size_t)m * G + g], fs[r]));
+        const double *row = scat + ((size_t)m * G + g) * G;
+        const int lo = band[((size_t)m * G + g) * 2], hi = band[((size_t)m * G + g) * 2 + 1];
+        for (int gg = lo; gg <= hi; gg++)
+            if (gg != g)
+                s_ = __dadd_rn(s_, __dmul_rn(row[gg], flux[(size_t)r * GP + gg]));
+        src[(size_t)r * GP + g] = s_;
+    }
+}
+
 // cmdo::CurrentCorrections::post_angle + calculate_corrections (correction_worker.hpp:223-246,
 // correction_worker.cpp:32-158) from the per-angle sums the TALLY == 2 sweep left behind.
 // One thread per (plane of this handle, sweep angle, coarse cell, direction).

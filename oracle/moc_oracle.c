@@ -35,6 +35,30 @@ void moc_oracle_self_scatter(int n_reg, const double *src, const double *flux, c
     }
 }
 
+void moc_oracle_fission_source(int n_reg, int n_group, double k, const double *xs_nf, const double *flux, double *fs)
+{
+    /* transport_sweeper.cpp:122-131: fission_source = 0; per region, per group, per FSR: += rkeff * xsnf[ig] * flux */
+    double rkeff = 1.0 / k;
+    for (int r = 0; r < n_reg; r++)
+        fs[r] = 0.0;
+    for (int g = 0; g < n_group; g++)
+        for (int r = 0; r < n_reg; r++)
+            fs[r] += rkeff * xs_nf[(size_t)g * n_reg + r] * flux[(size_t)r * n_group + g];
+}
+
+void moc_oracle_group_source(int n_reg, int n_group, int group, const double *ext, const double *xs_ch, const double *fs,
+                             const double *scat_to, const double *flux, double *src)
+{
+    for (int r = 0; r < n_reg; r++) {
+        double s = ext ? ext[r] : 0.0;  /* source.cpp:43-50 */
+        s += xs_ch[r] * fs[r];          /* source.cpp:71-76 */
+        for (int gg = 0; gg < n_group; gg++) /* source.cpp:97-108: the row's band in ascending order, self-scatter left out */
+            if (gg != group)
+                s += scat_to[(size_t)gg * n_reg + r] * flux[(size_t)r * n_group + gg];
+        src[r] = s;
+    }
+}
+
 /* BoundaryCondition::update(group, angle, out), boundary_condition.cpp:155-191 */
 static void bc_update_angle(const mocb200_problem *p, int a, double *in, const double *out)
 {

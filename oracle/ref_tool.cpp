@@ -148,6 +148,10 @@ public:
         out.put(p + "flux_in", fin);
         const VectorX &s = this->source_->get();
         out.put(p + "src", s.data(), {(uint64_t)s.size()});
+        // every group's flux as Source::in_scatter saw it when it built `src` (the swept group's own column is not
+        // read there): [n_reg][n_group]
+        std::vector<double> fall(this->flux_.begin(), this->flux_.end());
+        out.put(p + "flux_all", fall.data(), {(uint64_t)this->flux_.extent(0), (uint64_t)this->flux_.extent(1)});
         out.put(p + "bc_in", bc_in(group));
     }
     void record_source(ArrayFile &out, const std::string &p)
@@ -297,6 +301,14 @@ template <class SW> int run_golden(SW &sw, Source &source_ref, const std::string
     std::vector<double> khist;
     for (int outer = 0; outer < outers; outer++) {
         sw.calc_fission_source(k, fs);
+        { // inputs and result of TransportSweeper::calc_fission_source (transport_sweeper.cpp:119-134) for this outer
+            const ArrayB2 &fl = sw.flux();
+            std::vector<double> f0(fl.begin(), fl.end()), fsv(fs.begin(), fs.end());
+            const std::string o = "outer" + std::to_string(outer) + "_";
+            out.put(o + "flux_start", f0.data(), {(uint64_t)fl.extent(0), (uint64_t)fl.extent(1)});
+            out.put(o + "fission_source", fsv);
+            out.put_scalar<double>(o + "k", (double)k);
+        }
         sw.store_old_flux();
         for (int ig = 0; ig < ng; ig++) {
             source->initialize_group(ig);

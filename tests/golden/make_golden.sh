@@ -33,6 +33,8 @@ run mini3d_gs     mini3d.xml "0:0:0,0:1:1,1:2:1" --cmfd
 run mini3d_2d3d   mini3d.xml "0:0:1,0:2:1,1:1:1" --2d3d
 run 3x3_s05_gs    3x3.xml    "0:0:0,0:3:4,1:6:4" --cmfd --set solver/sweeper/rays@spacing=0.05
 ls -la "$HERE"/*.gz
+# SECTIONS=records regenerates only the sweep1g / source records above
+[ "${SECTIONS:-all}" = "records" ] && exit 0
 
 # whole-solve goldens: the reference solver stack with the reference CPU sweepers
 # (mocc_b200/bin/mocc_b200_solve = unmodified EigenSolver/CMFD/2D3D; <sweeper type> as in the input)

@@ -26,6 +26,10 @@ def oracle():
         lib.moc_oracle_exp.restype = C.c_double
         lib.moc_oracle_self_scatter.argtypes = [C.c_int] + [_f64p] * 5
         lib.moc_oracle_self_scatter.restype = None
+        lib.moc_oracle_fission_source.argtypes = [C.c_int, C.c_int, C.c_double, _f64p, _f64p, _f64p]
+        lib.moc_oracle_fission_source.restype = None
+        lib.moc_oracle_group_source.argtypes = [C.c_int, C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]
+        lib.moc_oracle_group_source.restype = None
         lib.moc_oracle_sweep1g.argtypes = [C.POINTER(Problem), C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p,
                                            _f64p, _f64p, _f64p]
         lib.moc_oracle_sweep1g_corrections.argtypes = [C.POINTER(Problem), C.c_int] + [_f64p] * 11
@@ -81,3 +85,28 @@ def oracle_sweep1g_corrections(arrays, xstr_split, xstr_true, qbar, sn_xs, bc_in
     if rc != 0:
         raise RuntimeError(f"oracle corrections sweep failed ({rc})")
     return flux, bc, cur, sf, alpha, beta
+
+
+def oracle_fission_source(k, xs_nf, flux):
+    """TransportSweeper::calc_fission_source: xs_nf [G][n_reg], flux [n_reg][G] -> fs [n_reg]."""
+    xs_nf = np.ascontiguousarray(xs_nf, dtype=np.float64)
+    flux = np.ascontiguousarray(flux, dtype=np.float64)
+    G, n_reg = xs_nf.shape
+    assert flux.shape == (n_reg, G)
+    fs = np.empty(n_reg)
+    oracle().moc_oracle_fission_source(n_reg, G, float(k), _p(xs_nf), _p(flux), _p(fs))
+    return fs
+
+
+def oracle_group_source(group, xs_ch, fs, scat_to, flux, ext=None):
+    """Source::initialize_group + fission + in_scatter: xs_ch [n_reg], scat_to [G][n_reg], flux [n_reg][G]."""
+    scat_to = np.ascontiguousarray(scat_to, dtype=np.float64)
+    flux = np.ascontiguousarray(flux, dtype=np.float64)
+    G, n_reg = scat_to.shape
+    xs_ch = np.ascontiguousarray(xs_ch, dtype=np.float64)
+    fs = np.ascontiguousarray(fs, dtype=np.float64)
+    ext = None if ext is None else np.ascontiguousarray(ext, dtype=np.float64)
+    src = np.empty(n_reg)
+    oracle().moc_oracle_group_source(n_reg, G, int(group), _p(ext) if ext is not None else None, _p(xs_ch), _p(fs),
+                                     _p(scat_to), _p(flux), _p(src))
+    return src

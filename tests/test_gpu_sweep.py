@@ -616,3 +616,90 @@ def test_angle_family_sharding_equals_whole_sweep(case, parts, tally):
         sw.close()
     assert not np.isnan(got_bc).any()
     _close(got_bc, ref_bc, rtol=1e-11)
+
+
+def _source_tables(gold, G):
+    from mocc_b200.capi import material_tables
+    xs_nf = np.stack([gold[f"xs_nf_{g}"] for g in range(G)])
+    xs_ch = np.stack([gold[f"xs_ch_{g}"] for g in range(G)])
+    xs_scat = np.stack([gold[f"xs_scat_to_{g}"].reshape(G, -1) for g in range(G)])  # [to][from][n_reg]
+    return xs_nf, xs_ch, xs_scat, material_tables(xs_nf, xs_ch, xs_scat)
+
+
+@pytest.mark.parametrize("case", ["mini2d_gs", "mini3d_gs", "3x3_s05_gs"])
+@pytest.mark.parametrize("external", [False, True])
+def test_device_source_construction_is_bit_identical_to_the_oracle(case, external):
+    """mocb200_fission_source / mocb200_build_source (calc_fission_source, Source::fission + in_scatter on the device)
+    against the oracle's restatement, which is pinned bit for bit on the reference's own sources: same bits."""
+    from oracle_lib import oracle_fission_source, oracle_group_source
+    flat, gold = load_case(case)
+    G, n_reg = (int(flat[k][0]) for k in ("n_group", "n_reg"))
+    xs_nf, xs_ch, xs_scat, (fsr_mat, t_nf, t_ch, t_scat) = _source_tables(gold, G)
+    assert t_nf.shape[0] < 16  # a handful of cross-section regions, not one per FSR
+    rng = np.random.default_rng(17)
+    flux = rng.uniform(0.2, 2.0, size=(G, n_reg))
+    ext = rng.uniform(0.0, 0.1, size=(G, n_reg)) if external else None
+    k = 1.0437
+    sw = _sweeper(flat)
+    with pytest.raises(RuntimeError):
+        sw.fission_source(k)  # no tables yet
+    sw.set_source_xs(fsr_mat, t_nf, t_ch, t_scat)
+    with pytest.raises(RuntimeError):
+        sw.build_source(0, 1)  # no fission source yet
+    sw.set_flux(0, flux)
+    sw.set_external_source(ext)
+    sw.fission_source(k)
+    fs = sw.get_fission_source()
+    fs_o = oracle_fission_source(k, xs_nf, flux.T)
+    assert np.array_equal(fs, fs_o)
+    sw.build_source(0, G)           # all groups at once: every group sees the same flux
+    src = sw.get_source(0, G)
+    for g in range(G):
+        s_o = oracle_group_source(g, xs_ch[g], fs_o, xs_scat[g], flux.T, ext=None if ext is None else ext[g])
+        assert np.array_equal(src[g], s_o)
+    # the host's fission source instead of the device's
+    sw.set_fission_source(2.0 * fs_o)
+    sw.build_source(1, 1)
+    s_o = oracle_group_source(1, xs_ch[1], 2.0 * fs_o, xs_scat[1], flux.T, ext=None if ext is None else ext[1])
+    assert np.array_equal(sw.get_source(1, 1)[0], s_o)
+    sw.close()
+
+
+@pytest.mark.parametrize("case", ["mini2d_gs", "3x3_s05_gs"])
+def test_fixed_source_step_with_device_sources_equals_host_sources(case):
+    """One FixedSourceSolver::step (fixed_source_solver.cpp:102-117) -- Gauss-Seidel over the groups, every group's
+    source built from the fluxes swept so far -- with the sources built on the device from the resident flux, against
+    the same step with the sources built on the host (oracle) and uploaded group by group."""
+    from oracle_lib import oracle_fission_source, oracle_group_source
+    flat, gold = load_case(case)
+    G, n_reg, bcpg = (int(flat[k][0]) for k in ("n_group", "n_reg", "bc_per_group"))
+    xs_nf, xs_ch, xs_scat, (fsr_mat, t_nf, t_ch, t_scat) = _source_tables(gold, G)
+    xstr = np.stack([gold[f"xs_tr_{g}"] for g in range(G)])
+    xself = np.stack([gold[f"xs_self_{g}"] for g in range(G)])
+    rng = np.random.default_rng(23)
+    flux0 = rng.uniform(0.5, 1.5, size=(G, n_reg))
+    bc = np.full((G, bcpg), 1.0 / (4.0 * np.pi))
+    k, n_inner = 0.97, 2
+    res = []
+    for device_sources in (True, False):
+        sw = _sweeper(flat, boundary_update=0)
+        sw.set_xs(0, xstr, xstr_src=xstr, xs_self=xself)
+        sw.set_flux(0, flux0)
+        sw.set_boundary(0, 0, bc)
+        if device_sources:
+            sw.set_source_xs(fsr_mat, t_nf, t_ch, t_scat)
+            sw.fission_source(k)
+            for g in range(G):
+                sw.build_source(g, 1)
+                sw.sweep(g, 1, n_inner=n_inner, tally_mode=1)
+        else:
+            fs = oracle_fission_source(k, xs_nf, flux0.T)
+            for g in range(G):
+                flux_now = sw.get_flux(0, G)
+                sw.set_source(g, oracle_group_source(g, xs_ch[g], fs, xs_scat[g], flux_now.T))
+                sw.sweep(g, 1, n_inner=n_inner, tally_mode=1)
+        res.append([sw.get_flux(0, G)] + [sw.get_boundary(0, g, 1)[0] for g in range(G)] +
+                   [x for g in range(G) for x in sw.get_coarse(g)])
+        sw.close()
+    for x, y in zip(*res):
+        _close(x, y, rtol=1e-12, atol=1e-14)
