@@ -584,6 +584,34 @@ def main():
                 "calls_per_step": len(comm_events), "bytes_per_call_per_rank": 8 * n_pack_max,
                 "ms_per_step": float(cm.item()), "share_of_e2e_step": float(cm.item()) / (float(t.item()) / args.steps * 1e3)}
         assert n_pack <= n_pack_max
+    # ---- the same step with the sources built ON THE DEVICE: per step the host sends k (a
+    #      call argument), the device computes the fission source and every group's fission + in-scatter source from the
+    #      resident flux (Gauss-Seidel over the groups, fixed_source_solver.cpp:102-117); downloads as before ----
+    e2e_dev = None
+    if world == 1 and all(k in arr for k in ("xs_nf", "xs_ch", "xs_scat")):
+        from mocc_b200.capi import material_tables
+        fsr_mat, t_nf, t_ch, t_scat = material_tables(arr["xs_nf"], arr["xs_ch"], arr["xs_scat"])
+        sw.set_source_xs(fsr_mat, t_nf, t_ch, t_scat)
+        blist0 = [bc_h[ip] for ip in range(n_plane)]
+
+        def step_e2e_device_sources():
+            sw.fission_source(1.0)
+            for g in range(G):
+                sw.build_source(g, 1)
+                sw.sweep(g, 1, n_inner=n_inner, tally_mode=TALLY_CURRENT)
+                sw.get_sweep_results(g, flux_h[g], [b[g] for b in blist0], coarse=True)
+        sw.set_flux(0, np.ones((G, n_reg)))
+        step_e2e_device_sources()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e_device_sources()
+        barrier()
+        dt = time.perf_counter() - t0
+        e2e_dev = {"value": updates_step * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": 8,
+                   "d2h_bytes_per_step": d2h, "materials": int(t_nf.shape[0]),
+                   "what": "fission source and group sources built on the device from the resident flux "
+                           "(mocb200_fission_source / mocb200_build_source); the host sends k"}
     # the clock sampler covers the device-resident AND the end-to-end timed regions (both under load)
     clocks = sampler.stop() if sampler else None
 
@@ -653,6 +681,7 @@ def main():
             "arm": {"kernel": kname, "resident_segments": n_useg, "bundled_segments": int(st["swept_segments"]),
                     "max_polar": args.max_polar or 2, "cache_groups": args.cache_groups or G},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e_device_sources": e2e_dev,
             "comm": comm,
             "gpu_launches": int(ln.item()),
             "clocks": clocks,

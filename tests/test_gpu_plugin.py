@@ -227,3 +227,18 @@ def test_jacobi_boundary_whole_solve_matches_reference(tmp_path):
     k = res["k_history"]
     assert k.size == 9, k
     assert abs(k[-1] - 0.3179551223) < 1e-8, k[-1]
+
+
+@pytest.mark.parametrize("name", ["test_MoC_IHM", "test_MoCSweeper"])
+def test_reference_unit_tests_pass_on_the_cuda_sweeper(tmp_path, name):
+    """The reference's OWN MoC unit tests (src/sweepers/moc/tests/test_MoC_IHM.cpp:136-147: infinite homogeneous
+    medium, 800 inners per group, flux within 0.5 % of the analytic spectrum; test_MoCSweeper.cpp:58-94: pin-flux
+    get / set / get round trip), compiled from the reference's unmodified sources with every `MoCSweeper` they
+    name bound to CudaMoCSweeper (mocc_b200/host/tests/ref_test_on_cuda.hpp, built by mocc_b200/host/Makefile)."""
+    exe = os.path.join(ROOT, "mocc_b200", "bin", "tests", name + "_cuda")
+    assert os.path.exists(exe), f"{exe} missing: run __graft_entry__.build() where the reference sources are"
+    shutil.copy(os.path.join(ROOT, "mocc_b200", "bin", "inputs", "c5g7.xsl"), tmp_path)
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    tail = r.stdout[-1500:] + r.stderr[-1500:]
+    assert r.returncode == 0, tail
+    assert "Success: 1 tests passed" in r.stdout, tail
