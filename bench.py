@@ -64,6 +64,10 @@ WORKLOADS = {
     "dense_a": ("C5G7 2-D dense-A (examples/c5g7_2d.xml with cg 16x4, spacing 0.02): 7 groups, n_inner 10, "
                 "coarse-current tally on the last inner",
                 ["solver/ang_quad@n_azimuthal=16", "solver/ang_quad@n_polar=4", "solver/sweeper/rays@spacing=0.02"]),
+    # SURVEY.md 8(d) "dense-B" (~x40 segments: S ~ 7.3e8, the attenuation cache of all 7 groups is ~41 GB)
+    "dense_b": ("C5G7 2-D dense-B (examples/c5g7_2d.xml with cg 32x4, spacing 0.01): 7 groups, n_inner 10, "
+                "coarse-current tally on the last inner",
+                ["solver/ang_quad@n_azimuthal=32", "solver/ang_quad@n_polar=4", "solver/sweeper/rays@spacing=0.01"]),
     # BASELINE.json configs[4] at plane level: 9x9 checkerboard of the C5G7 assemblies with a reflector ring
     # (tools/make_quarter_core.py); with --gpus N one such plane per GPU
     "quarter_core": ("synthetic quarter core, 9x9 assemblies of 17x17 pins (C5G7 lattices, cg 8x2, spacing 0.05): "

@@ -1,6 +1,8 @@
 #include "cuda_moc_sweeper.hpp"
 
+#include <cctype>
 #include <chrono>
+#include <cstring>
 #include <cstdio>
 
 #include <algorithm>
@@ -45,6 +47,7 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
     opt.max_polar           = cu.attribute("max_polar").as_int(0);
     opt.cache_groups        = cu.attribute("cache_groups").as_int(0);
     group_batch_            = cu.attribute("group_batch").as_bool(false);
+    device_sources_         = cu.attribute("device_sources").as_bool(true);
     std::string kernel      = cu.attribute("kernel").as_string("auto");
     if (kernel == "auto")
         opt.kernel = MOCB200_KERNEL_AUTO;
@@ -137,6 +140,7 @@ CudaMoCSweeper::CudaMoCSweeper(const pugi::xml_node &input, const CoreMesh &mesh
         }
     }
     xs_uploaded_.assign(n_group_, false);
+    flux_stale_.assign(n_group_, true);
     col_.resize(std::max<size_t>(n_reg_, (size_t)n_bc_));
     cur_.resize(mesh_.n_surf());
     sflux_.resize(mesh_.n_surf());
@@ -199,6 +203,85 @@ const mocb200_stats &CudaMoCSweeper::device_stats()
     return stats_;
 }
 
+// ---- device-side sources ----
+void DeviceSource::initialize_group(int ig)
+{
+    mocc::Source::initialize_group(ig); // external source or zero (source.cpp:41-54)
+    group_     = ig;
+    fs_        = nullptr;
+    scattered_ = false;
+}
+
+void DeviceSource::fission(const mocc::ArrayB1 &fs, int ig)
+{
+    fs_ = &fs; // chi_g * fs is added on the device (source.cpp:64-80)
+    if (has_external_ || check_)
+        mocc::Source::fission(fs, ig);
+}
+
+void DeviceSource::in_scatter(size_t ig)
+{
+    scattered_ = true; // sum over g' != g of Sigma_s(g' -> g) flux_g' is added on the device (source.cpp:86-112)
+    if (has_external_ || check_)
+        mocc::Source::in_scatter(ig);
+}
+
+mocc::UP_Source_t CudaMoCSweeper::create_source(const pugi::xml_node &input) const
+{
+    if (!device_sources_ || group_batch_ || !device_sources_allowed())
+        return mocc::moc::MoCSweeper::create_source(input);
+    // SourceFactory (source_factory.cpp:26-69) with the P0 source replaced
+    std::string scat = input.attribute("scattering").value();
+    for (auto &c : scat)
+        c = (char)std::tolower(c);
+    if (input.empty() || scat != "p0")
+        return mocc::moc::MoCSweeper::create_source(input); // the reference's own error handling
+    mocc::UP_Source_t source(
+        new DeviceSource((int)n_reg_, xs_mesh_.get(), this->flux(), std::getenv("MOCB200_CHECK_DEVICE_SOURCES") != nullptr));
+    source->add_external(input);
+    return source;
+}
+
+void CudaMoCSweeper::initialize()
+{
+    mocc::moc::MoCSweeper::initialize();
+    flux_stale_.assign(n_group_, true);
+}
+
+mocc::real_t CudaMoCSweeper::set_pin_flux_1g(int group, const mocc::ArrayB1 &pin_flux, mocc::MeshTreatment treatment)
+{
+    flux_stale_[group] = true;
+    return mocc::moc::MoCSweeper::set_pin_flux_1g(group, pin_flux, treatment);
+}
+
+// cross sections by cross-section-mesh region for the device's fission / in-scatter sources
+void CudaMoCSweeper::upload_source_tables()
+{
+    const int ng = (int)n_group_;
+    std::vector<int32_t> fsr_mat(n_reg_, 0), band;
+    std::vector<double> nf, ch, scat;
+    int m = 0;
+    for (const auto &xsr : *xs_mesh_) {
+        for (int g = 0; g < ng; g++) {
+            nf.push_back(xsr.xsmacnf(g));
+            ch.push_back(xsr.xsmacch(g));
+            const mocc::ScatteringRow &row = xsr.xsmacsc().to(g);
+            band.push_back(row.min_g);
+            band.push_back(row.max_g);
+            for (int gf = 0; gf < ng; gf++)
+                scat.push_back(gf >= row.min_g && gf <= row.max_g ? row[gf] : 0.0);
+        }
+        for (const int ireg : xsr.reg())
+            fsr_mat[ireg] = m;
+        m++;
+    }
+    for_each_part([&](const Part &p, size_t) {
+        check(p, mocb200_set_source_xs(p.h, m, fsr_mat.data(), nf.data(), ch.data(), scat.data(), band.data()),
+              "mocb200_set_source_xs");
+    });
+    source_xs_sent_ = true;
+}
+
 // Host state of one group -> device: cross sections (when they can have changed), the
 // one-group source, the current scalar flux and the incoming boundary flux.
 void CudaMoCSweeper::upload_group(int group)
@@ -216,12 +299,58 @@ void CudaMoCSweeper::upload_group(int group)
                   "mocb200_set_xs");
         });
     xs_uploaded_[group] = true;
-    for (int ireg = 0; ireg < (int)n_reg_; ireg++)
-        col_[ireg] = flux_(ireg, group);
-    // source, flux and incoming boundary flux in one staged copy per device (no synchronisation)
     std::vector<const double *> bc(n_macroplane_, nullptr);
     for (int ip = 0; ip < n_macroplane_; ip++)
         bc[ip] = boundary_[ip].get_boundary(group, 0).second;
+    DeviceSource *ds = dynamic_cast<DeviceSource *>(source_);
+    if (ds && ds->deferred(group)) {
+        // The device builds this group's source from the flux resident there: the host sends the fission source
+        // (once per outer: the solver recomputes it before group 0, eigen_solver.cpp:229-231) and the flux columns it
+        // has rewritten since the device last had them (after initialize() and after the CMFD prolongation: all of
+        // them, once per outer; none inside a fixed-source iteration).
+        if (!source_xs_sent_)
+            upload_source_tables();
+        const int ng = (int)n_group_;
+        for (int g = 0; g < ng; g++) {
+            if (!flux_stale_[g])
+                continue;
+            for (int ireg = 0; ireg < (int)n_reg_; ireg++)
+                col_[ireg] = flux_(ireg, g);
+            for_each_part([&](const Part &p, size_t) { check(p, mocb200_set_flux(p.h, g, 1, col_.data()), "mocb200_set_flux"); });
+            flux_stale_[g] = false;
+        }
+        if (group == 0 || !fs_sent_) {
+            flux_all_.assign(n_reg_, 0.0); // no fission source (fixed-source problem): zero
+            if (ds->fs())
+                std::copy(ds->fs()->begin(), ds->fs()->end(), flux_all_.begin());
+            for_each_part([&](const Part &p, size_t) {
+                check(p, mocb200_set_fission_source(p.h, flux_all_.data()), "mocb200_set_fission_source");
+            });
+            fs_sent_ = true;
+        }
+        for_each_part([&](const Part &p, size_t) {
+            check(p, mocb200_build_source(p.h, group, 1), "mocb200_build_source");
+            check(p, mocb200_set_sweep_inputs(p.h, group, nullptr, nullptr, bc.data()), "mocb200_set_sweep_inputs");
+        });
+        if (ds->check()) { // the host built its source too: every bit must agree
+            std::vector<double> dev(n_reg_);
+            const Part &p = parts_[0];
+            check(p, mocb200_get_source(p.h, group, 1, dev.data()), "mocb200_get_source");
+            for (int ireg = p.reg_lo; ireg < p.reg_hi; ireg++)
+                if (std::memcmp(&dev[ireg], &src.data()[ireg], sizeof(double)) != 0) {
+                    std::stringstream msg;
+                    msg << "device-built source of group " << group << " differs from the host's in FSR " << ireg << ": "
+                        << std::setprecision(17) << dev[ireg] << " vs " << src.data()[ireg];
+                    throw EXCEPT(msg.str());
+                }
+            n_source_checks_++;
+        }
+        return;
+    }
+    for (int ireg = 0; ireg < (int)n_reg_; ireg++)
+        col_[ireg] = flux_(ireg, group);
+    flux_stale_[group] = false;
+    // source, flux and incoming boundary flux in one staged copy per device (no synchronisation)
     for_each_part([&](const Part &p, size_t) {
         check(p, mocb200_set_sweep_inputs(p.h, group, src.data(), col_.data(), bc.data()), "mocb200_set_sweep_inputs");
     });

@@ -35,12 +35,56 @@
 
 namespace mocc_b200 {
 
+// The Source CudaMoCSweeper::create_source hands to MOCC's FixedSourceSolver. The solver still
+// calls initialize_group / fission / in_scatter before every sweep(group) (fixed_source_solver.cpp:102-117), but the
+// O(n_reg G) host loops of Source::fission and Source::in_scatter (source.cpp:64-112) are not run: the calls are
+// recorded and CudaMoCSweeper::sweep has the device build the same source from the flux resident there
+// (mocb200_set_fission_source + mocb200_build_source, bit-identical). With an external source, or when anything adds
+// to the host source behind the device's back, the reference's host path is used as it is.
+class DeviceSource : public mocc::SourceIsotropic {
+public:
+    DeviceSource(int nreg, const mocc::XSMesh *xs_mesh, const mocc::ArrayB2 &flux, bool check)
+        : mocc::SourceIsotropic(nreg, xs_mesh, flux), check_(check)
+    {
+    }
+    void initialize_group(int ig) override;
+    void fission(const mocc::ArrayB1 &fs, int ig) override;
+    void in_scatter(size_t ig) override;
+    // true: the source of `group` is to be built on the device (fission source: fs(), nullptr = none)
+    bool deferred(int group) const
+    {
+        return !has_external_ && group_ == group && scattered_;
+    }
+    const mocc::ArrayB1 *fs() const
+    {
+        return fs_;
+    }
+    bool check() const // MOCB200_CHECK_DEVICE_SOURCES: the host builds its source too, the sweeper compares every bit
+    {
+        return check_;
+    }
+
+private:
+    const mocc::ArrayB1 *fs_ = nullptr;
+    int group_               = -1;
+    bool scattered_          = false;
+    bool check_              = false;
+};
+
 class CudaMoCSweeper : public mocc::moc::MoCSweeper {
 public:
     CudaMoCSweeper(const pugi::xml_node &input, const mocc::CoreMesh &mesh);
     ~CudaMoCSweeper();
 
     void sweep(int group) override;
+
+    // moc_sweeper.hpp:90-95 (`final` there: nofinal_moc_sweeper.hpp): a DeviceSource when sources are built on the
+    // device (<cuda device_sources="t">, the default of type="moc_cuda" without group batching)
+    mocc::UP_Source_t create_source(const pugi::xml_node &input) const override;
+    // the host rewrites the flux (moc_sweeper.cpp:234-253, 360-433): the device copy is refreshed before the next source
+    void initialize() override;
+    mocc::real_t set_pin_flux_1g(int group, const mocc::ArrayB1 &pin_flux,
+                                 mocc::MeshTreatment treatment = mocc::MeshTreatment::PIN_PLANE) override;
 
     // Device time spent in transport-sweep kernels / number of C-ABI sweeps so far
     double device_sweep_ms() const
@@ -85,6 +129,17 @@ protected:
 
     std::vector<Part> parts_;
     bool group_batch_ = false;
+    // device-side sources
+    bool device_sources_ = false; // <cuda device_sources="t|f"> (default t)
+    virtual bool device_sources_allowed() const // the 2D3D variant adds transverse leakage to the host source
+    {
+        return true;
+    }
+    bool source_xs_sent_ = false, fs_sent_ = false;
+    long n_source_checks_ = 0;
+    std::vector<bool> flux_stale_; // per group: the host has rewritten the column since the device last had it
+    std::vector<double> flux_all_;
+    void upload_source_tables();
     int n_bc_             = 0; // boundary values per group per plane
     int n_macroplane_     = 0;
     // per-FSR cross sections, [n_group][n_reg]
@@ -126,6 +181,10 @@ protected:
     bool split_last_inner() const override
     {
         return true;
+    }
+    bool device_sources_allowed() const override
+    {
+        return false;
     }
     void before_last_inner(int group) override;
     void post_group(int group, int tally) override;

@@ -242,3 +242,17 @@ def test_reference_unit_tests_pass_on_the_cuda_sweeper(tmp_path, name):
     tail = r.stdout[-1500:] + r.stderr[-1500:]
     assert r.returncode == 0, tail
     assert "Success: 1 tests passed" in r.stdout, tail
+
+
+@pytest.mark.parametrize("xml,gold", [("mini2d.xml", "mini2d_solve_ref.arrays.gz"), ("3x3.xml", "3x3_solve_ref.arrays.gz")])
+def test_device_built_sources_are_bit_identical_inside_the_solve(tmp_path, xml, gold):
+    """type="moc_cuda" leaves Source::fission / in_scatter to the device (DeviceSource, SURVEY.md 8f row 1). With
+    MOCB200_CHECK_DEVICE_SOURCES the host builds every source too and the sweeper throws on the first differing
+    bit: the whole eigenvalue solve runs through, and still equals the reference's."""
+    res = _solve(tmp_path, xml, ["solver/sweeper@type=moc_cuda"], extra_env={"MOCB200_CHECK_DEVICE_SOURCES": "1"})
+    _check(res, _golden(gold), 1e-9, 1e-8)
+
+
+def test_host_built_sources_remain_selectable(tmp_path):
+    res = _solve(tmp_path, "3x3.xml", ["solver/sweeper@type=moc_cuda", "solver/sweeper/cuda@device_sources=f"])
+    _check(res, _golden("3x3_solve_ref.arrays.gz"), 1e-9, 1e-8)
