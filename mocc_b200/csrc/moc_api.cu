@@ -918,8 +918,8 @@ int build(mocb200_sweeper *h, const mocb200_problem &p)
                 xptr[(size_t)(pbegin[t] + k0) / 4] = make_int2(cf, bw_first[k0 / 4]);
             }
         }
-        xcross.push_back(sentinel); // the kernels read up to two entries past the one they test
-        xcross.push_back(sentinel);
+        for (int i = 0; i < 6; i++) // the kernels read ahead of the entry they test (RCHUNK: up to three past a sentinel)
+            xcross.push_back(sentinel);
         int rc2;
         if ((rc2 = dev_upload(h, &h->d_pseg_len, plen)) || (rc2 = dev_upload(h, &h->d_pseg_fsr, pfsr)) ||
             (rc2 = dev_upload(h, &h->d_xptr, xptr)) || (rc2 = dev_upload(h, &h->d_xcross, xcross)))
@@ -1394,7 +1394,10 @@ RcFn pick_rc_kernel(int np, int tally, const RcConfig &c)
 
 RcConfig rc_tally_config(int np, int tally, const RcConfig &c)
 {
-    if (tally == 0 || c.TEAMS <= 3) // three four-warp teams leave 168 registers per thread: no spills
+    static const char *tt = getenv("MOCB200_RC_TALLY_TEAMS"); // A/B hook: teams per CTA of the tallying variants
+    if (tally != 0 && tt && atoi(tt) >= 1 && pick_rc_kernel(np, tally, RcConfig{c.LMAX, c.NW, atoi(tt)}))
+        return RcConfig{c.LMAX, c.NW, atoi(tt)};
+    if (tally == 0 || c.TEAMS <= 3) // three four-warp teams leave 168 registers per thread
         return c;
     const RcConfig t{c.LMAX, c.NW, c.TEAMS - 1};
     return (t.TEAMS >= 1 && pick_rc_kernel(np, tally, t)) ? t : c;

@@ -442,7 +442,12 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
         const int lim_f  = (k0 + len == nseg) ? len : len - 1; // highest relative node this chunk tallies, forward
         int ci_f = 0, ci_b = 0;
         int rf = INT32_MAX, rb = INT32_MIN;
+        // The crossing lists live in global memory. xf / xb: the crossing being waited for; f1, f2 / b1, b2: the two
+        // behind it, requested before they are needed -- a crossing consumed inside the serial walk used to cost one
+        // dependent L2 round trip each (the tallying inner ran 2.5x the plain one, profiles/r2/tuning.md). Reads run
+        // up to three entries past a list's sentinel: the array is padded accordingly (build, moc_api.cu).
         Cross xf{INT32_MAX, 0}, xb{INT32_MAX, 0};
+        Cross f1{INT32_MAX, 0}, f2{INT32_MAX, 0}, b1{INT32_MAX, 0}, b2{INT32_MAX, 0};
         auto set_f = [&]() {
             const int r = xf.node - k0;
             rf          = (xf.node != INT32_MAX && r <= lim_f) ? r : INT32_MAX;
@@ -453,16 +458,27 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
         };
         if (len > 0) {
             xf = xfl[0], xb = xbl[0];
+            f1 = xfl[1], b1 = xbl[1];
+            f2 = xfl[2], b2 = xbl[2];
             set_f();
             set_b();
         }
+        auto next_f = [&]() {
+            xf = f1, f1 = f2, f2 = xfl[ci_f + 3];
+            ++ci_f;
+            set_f();
+        };
+        auto next_b = [&]() {
+            xb = b1, b1 = b2, b2 = xbl[ci_b + 3];
+            ++ci_b;
+            set_b();
+        };
         double s[LMAX];
 #pragma unroll
         for (int k = 0; k < LMAX; k++) {
             while (rf == k) { // the forward flux at the node in front of position k
                 tally_cross(xf, psi_f, 0);
-                xf = xfl[++ci_f];
-                set_f();
+                next_f();
             }
             const double d = (psi_f - qv[k]) * ome[k];
             psi_f -= d;
@@ -472,16 +488,14 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
         }
         while (rf == LMAX) { // far end of the ray behind a full last chunk
             tally_cross(xf, psi_f, 0);
-            xf = xfl[++ci_f];
-            set_f();
+            next_f();
         }
         double *al = ab + (size_t)c * LMAX * P + p;
 #pragma unroll
         for (int k = LMAX - 1; k >= 0; k--) {
             while (rb == k) {
                 tally_cross(xb, psi_b, 1);
-                xb = xbl[++ci_b];
-                set_b();
+                next_b();
             }
             const double d = (psi_b - qv[k]) * ome[k];
             psi_b -= d;
@@ -491,8 +505,7 @@ __device__ __forceinline__ int rc_sweep_body(const RcArgs &a, uint64_t *s_bar, d
         }
         while (rb == -1) { // near end of the ray
             tally_cross(xb, psi_b, 1);
-            xb = xbl[++ci_b];
-            set_b();
+            next_b();
         }
     };
     auto store_exit = [&](const Item &it, int enc, double v) {
