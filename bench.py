@@ -624,14 +624,14 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "c5g7_2d" and os.path.exists(REF_TOOL):
         cores = os.cpu_count() or 1
         env = dict(os.environ, OMP_NUM_THREADS=str(cores))
-        out = subprocess.run([REF_TOOL, "time", "c5g7_2d.xml", "--cmfd", "--sweeps", "1", "--warmup", "0"],
+        out = subprocess.run([REF_TOOL, "time", "c5g7_2d.xml", "--cmfd", "--sweeps", "2", "--warmup", "1"],
                              cwd=os.path.join(ROOT, "oracle", "_ref", "inputs"), env=env, capture_output=True,
                              text=True)
         js = [x for x in out.stdout.splitlines() if x.startswith("{")]
         if js:
             r = json.loads(js[-1])
             cpu = {"value": r["updates_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
-                   "sample": f"one step of the same workload (7 groups x {r['n_inner']} inners, moc::Current on the "
+                   "sample": f"two steps (after one warm-up step) of the same workload (7 groups x {r['n_inner']} inners, moc::Current on the "
                              f"last inner): {r['updates']:.3e} updates in {r['seconds']:.2f} s, reference MoCSweeper "
                              f"(OpenMP, unmodified sources in oracle/_ref)"}
 

@@ -308,8 +308,9 @@ typedef struct mocb200_stats {
 } mocb200_stats;
 int mocb200_get_stats(const mocb200_sweeper *h, mocb200_stats *out);
 
-/* Time (ms, CUDA events on the handle's stream) spent in transport-sweep kernels by the last
- * mocb200_sweep call; synchronises. */
+/* Time (ms, CUDA events on the handle's stream) of the sweep kernels of the LAST inner iteration of the last
+ * mocb200_sweep call (the tallying one when a tally was requested; with mocb200_options.persistent and no tally: the
+ * whole persistent launch); synchronises. For the time of every inner use mocb200_set_timing / mocb200_get_timing. */
 int mocb200_last_sweep_ms(mocb200_sweeper *h, double *ms);
 
 /*

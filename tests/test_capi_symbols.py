@@ -67,3 +67,20 @@ def test_flatfile_roundtrip(tmp_path):
     assert list(back) == list(flat)
     for k in flat:
         assert back[k].dtype == flat[k].dtype and np.array_equal(back[k], flat[k])
+
+
+def test_material_tables_reproduce_the_per_fsr_cross_sections():
+    """capi.material_tables: cross-section-mesh regions out of per-FSR arrays (the form mocb200_set_source_xs takes)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from conftest import load_case
+    from mocc_b200.capi import material_tables
+    flat, gold = load_case("3x3_s05_gs")
+    G = int(flat["n_group"][0])
+    xs_nf = np.stack([gold[f"xs_nf_{g}"] for g in range(G)])
+    xs_ch = np.stack([gold[f"xs_ch_{g}"] for g in range(G)])
+    xs_scat = np.stack([gold[f"xs_scat_to_{g}"].reshape(G, -1) for g in range(G)])
+    fsr_mat, t_nf, t_ch, t_scat = material_tables(xs_nf, xs_ch, xs_scat)
+    assert fsr_mat.dtype == np.int32 and fsr_mat.size == xs_nf.shape[1] and 1 < t_nf.shape[0] <= 8
+    assert np.array_equal(t_nf[fsr_mat].T, xs_nf) and np.array_equal(t_ch[fsr_mat].T, xs_ch)
+    assert np.array_equal(np.moveaxis(t_scat[fsr_mat], 0, 2), xs_scat)
