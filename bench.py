@@ -2,6 +2,7 @@
 """bench.py -- throughput of the MoC transport sweep on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--mode pergroup|batched] [--impl reference]
+                    [--shard planes|angles] [--workload c5g7_2d|dense_a|dense_b|quarter_core] [--persistent 0|1|2]
 
 Workload (config.workload): C5G7 2-D, `examples/c5g7_2d.xml` as shipped by the reference
 (7 groups, Chebyshev-Gauss 8x2 per octant, ray spacing 0.05 cm, n_inner = 10, CMFD on so the
@@ -14,6 +15,10 @@ updates (S = reference segment count, polar copies counted).
   e2e     the same step through the C ABI with HOST buffers: per group the one-group source,
           scalar flux and boundary flux go host->device and flux, boundary flux and coarse
           tallies come back, exactly what the C++ plugin (mocc_b200/host) does per sweep(group)
+  e2e_device_sources  the same step with the sources built ON THE DEVICE from the resident flux
+          (mocb200_fission_source / mocb200_build_source): the host sends k, downloads as in e2e
+  e2e_plugin, time_to_converge_s   MOCC's own eigenvalue solve of the same input through the C++ plugin
+          (<sweeper type="moc_cuda">) next to the reference sweeper on the box's host cores
   mode    pergroup: one mocb200_sweep per group (the reference's sweep(group) contract,
           Gauss-Seidel in energy); batched: all groups in one mocb200_sweep (8 group lanes)
 
@@ -25,6 +30,10 @@ packed on the device (mocb200_pack_results_device) and exchanged with ONE NCCL a
 then copied to pinned host memory (everything on rank 0, where a single-process host solver would run; the own
 planes on the other ranks); `comm` reports the device time of those all-gathers
 (scaling "weak": one plane per GPU).
+--shard angles (N > 1): ONE plane, rank r sweeps its angle families (mocb200_angle_families: closed under the boundary
+update, so the Gauss-Seidel boundary order is kept and no boundary flux travels); after every inner sweep one NCCL
+all-reduce sums the per-FSR tally on the device buffer the handle adopted, then every rank applies the flux update
+(scaling "strong": the total work is fixed).
 
 --impl reference times the UNMODIFIED reference CPU sweeper (oracle/_ref/ref_tool, OpenMP on
 all host cores) on the same input; rank 0 only.
