@@ -347,6 +347,15 @@ void CudaMoCSweeper::upload_group(int group)
         }
         return;
     }
+    if (ds && !ds->host_built()) {
+        // sweep(group) without initialize_group / in_scatter for THIS group right before it (FixedSourceSolver::step
+        // always does both): the host array holds no fission / in-scatter source to fall back to
+        std::stringstream msg;
+        msg << "CudaMoCSweeper::sweep(" << group << "): the source of this group was not prepared (Source::initialize_group "
+               "and in_scatter must precede the sweep when sources are built on the device; <cuda device_sources=\"f\"/> "
+               "restores host-built sources)";
+        throw EXCEPT(msg.str());
+    }
     for (int ireg = 0; ireg < (int)n_reg_; ireg++)
         col_[ireg] = flux_(ireg, group);
     flux_stale_[group] = false;

@@ -59,6 +59,11 @@ public:
     {
         return fs_;
     }
+    // false: Source::get() does not hold this group's fission / in-scatter source (they were left to the device)
+    bool host_built() const
+    {
+        return has_external_ || check_;
+    }
     bool check() const // MOCB200_CHECK_DEVICE_SOURCES: the host builds its source too, the sweeper compares every bit
     {
         return check_;
