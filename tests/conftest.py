@@ -37,6 +37,8 @@ CASES = {
     "mini3d_gs": ("mini3d_gs.mocflat.gz", "mini3d_gs.golden.gz"),
     "3x3_s05_gs": ("3x3_s05_gs.mocflat.gz", "3x3_s05_gs.golden.gz"),
     "mini3d_2d3d": ("mini3d_gs.mocflat.gz", "mini3d_2d3d.golden.gz"),
+    # geometry and cross sections of the reference's analytic test (test_MoC_IHM.cpp)
+    "ihm": ("ihm.mocflat.gz", "ihm.golden.gz"),
 }
 
 _cache = {}

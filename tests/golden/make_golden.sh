@@ -32,6 +32,9 @@ run mini3d_gs     mini3d.xml "0:0:0,0:1:1,1:2:1" --cmfd
 # MoCSweeper_2D3D + cmdo::CurrentCorrections (self-coupled): last inner records alpha/beta
 run mini3d_2d3d   mini3d.xml "0:0:1,0:2:1,1:1:1" --2d3d
 run 3x3_s05_gs    3x3.xml    "0:0:0,0:3:4,1:6:4" --cmfd --set solver/sweeper/rays@spacing=0.05
+# geometry + cross sections of the reference's analytic test case (test_MoC_IHM.cpp): the oracle is run on it to the
+# analytic infinite-medium spectrum in tests/test_oracle.py
+run ihm           ihm.xml    "0:0:0"
 ls -la "$HERE"/*.gz
 # SECTIONS=records regenerates only the sweep1g / source records above
 [ "${SECTIONS:-all}" = "records" ] && exit 0

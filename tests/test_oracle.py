@@ -109,3 +109,36 @@ def test_oracle_source_construction_is_bit_identical_to_the_reference(case):
         g, o = int(rec["group"][0]), int(rec["outer"][0])
         src = oracle_group_source(g, gold[f"xs_ch_{g}"], fs_of[o], gold[f"xs_scat_to_{g}"].reshape(G, -1), rec["flux_all"])
         assert np.array_equal(src, rec["src"])
+
+
+def test_oracle_reaches_the_analytic_infinite_medium_spectrum():
+    """The reference's own known-answer test of the sweep (src/sweepers/moc/tests/test_MoC_IHM.cpp:99-147), run on
+    the ORACLE: infinite homogeneous medium (UO2-3.3, all boundaries reflective, LS-2, spacing 0.01), flux set to the
+    analytic spectrum phi = M^-1 chi (M = diag(Sigma_tr) - Sigma_s, :160-181), fission source = 1 in every region, then
+    group by group the reference's source construction and 800 inner iterations of self scatter + sweep: every FSR flux
+    within 0.5 % of phi_g, the reference's tolerance (:141-144). The same test runs on the CUDA sweeper itself in
+    tests/test_gpu_plugin.py (compiled from the reference's unmodified source)."""
+    from oracle_lib import oracle_fission_source, oracle_group_source, oracle_self_scatter
+    flat, gold = load_case("ihm")
+    G, n_reg = int(flat["n_group"][0]), int(flat["n_reg"][0])
+    assert G == 7 and n_reg == 54 and int(gold["n_inner"][0]) == 800
+    tr = np.array([gold[f"xs_tr_{g}"][0] for g in range(G)])
+    nf = np.array([gold[f"xs_nf_{g}"][0] for g in range(G)])
+    chi = np.array([gold[f"xs_ch_{g}"][0] for g in range(G)])
+    scat = np.array([gold[f"xs_scat_to_{g}"].reshape(G, -1)[:, 0] for g in range(G)])  # [to][from]
+    phi = np.linalg.solve(np.diag(tr) - scat, chi)
+    k_inf = float(nf @ phi)
+    assert 0.5 < k_inf < 1.5 and np.all(phi > 0)  # 0.7382: what the reference solve of this input converges to as well
+    xs_nf = np.stack([gold[f"xs_nf_{g}"] for g in range(G)])
+    flux = np.tile(phi, (n_reg, 1))                      # [n_reg][G], the true spectrum (set_spectrum, :84-92)
+    fs = oracle_fission_source(k_inf, xs_nf, flux)
+    assert np.max(np.abs(fs - 1.0)) < 1e-14              # :127-129
+    bc = np.zeros((G, int(flat["n_plane"][0]), int(flat["bc_per_group"][0])))
+    for g in range(G):
+        src = oracle_group_source(g, gold[f"xs_ch_{g}"], fs, gold[f"xs_scat_to_{g}"].reshape(G, -1), flux)
+        f, b = flux[:, g].copy(), bc[g]
+        for _ in range(800):
+            q = oracle_self_scatter(src, f, gold[f"xs_self_{g}"], gold[f"xs_tr_{g}"])
+            f, b, _, _ = oracle_sweep1g(flat, gold[f"xs_tr_{g}"], q, b, gs_boundary=True)
+        flux[:, g] = f
+        assert np.max(np.abs(f - phi[g])) < 0.005 * phi[g], f"group {g}: {np.max(np.abs(f - phi[g]) / phi[g]):.3e}"
